@@ -1,0 +1,471 @@
+// Implicit-GEMM convolution for the NCSN++ ResBlocks on Blackwell tensor cores (sm_100a).
+//
+//   out[b,h,w,n] = epilogue( sum_{tap,c} A[b, h+dy(tap), w+dx(tap), c] * Wt[n, tap, c]  (+ 1x1 shortcut blocks) )
+//
+// Replaces the cuDNN/oneDNN convolutions behind nn.Conv2d in the reference's ResnetBlockBigGANpp
+// (/root/reference/flowmse/backbones/ncsnpp_utils/layerspp.py:259-270; conv constructors layers.py:100-124).
+//
+// Design (B200-first, not a translation of any library kernel):
+//  * Activations are NHWC.  One CTA owns a 128-pixel (TH x TW) x BN-channel output tile; the accumulator lives in
+//    TMEM (128 lanes x BN fp32 columns).
+//  * No im2col: for every filter tap the A tile is ONE 5-D TMA box {64 ch, TW, TH, 1, 1} fetched at the shifted
+//    coordinate (w0+dx, h0+dy); TMA's out-of-bounds zero fill IS the conv padding.  TMA writes the tile with the
+//    128-byte swizzle, which is exactly the K-major SWIZZLE_128B layout tcgen05.mma consumes.
+//  * fp32 parity on fp16 tensor cores: every operand is carried as an exact hi/lo fp16 pair (x = hi + lo, 22 bits
+//    of significand); per K step three MMAs are issued, A_hi*B_hi + A_hi*B_lo + A_lo*B_hi, accumulating in fp32.
+//    The dropped lo*lo term is ~2^-22 relative.  Weights are pre-scaled by a power of two per conv so the lo parts
+//    stay in the fp16 normal range; the scale is undone in the epilogue.
+//  * The ResBlock's 1x1 shortcut conv (Conv_2) is folded into the second 3x3 conv as extra K blocks read from a
+//    second tensor map, so (x_shortcut + h)/sqrt(2) costs no extra pass.
+//  * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
+//    warps 2..5 = epilogue (TMEM -> registers -> bias/residual/scale -> global).
+#include "flowse_internal.h"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace flowse {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // fp16 elements per K block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int NUM_THREADS = 192;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN >= 128) ? 3 : 5;
+  static constexpr int TMEM_COLS = (BN < 32) ? 32 : BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+};
+
+struct GemmParams {
+  int H, W, TW, TH, tiles_w, tiles_h;
+  int nchunk_main, ntaps, nchunk_sc;
+  int Cout, ldc;
+  float wscale_inv;
+  const float* bias;
+  int bias_bstride;
+  const float* residual;
+  float* out;
+  int div_sqrt2;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX,
+                         const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * C::STAGES + 1];     // full[STAGES], empty[STAGES], tmem_full
+  __shared__ uint32_t tmem_slot_var;
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = ptx::smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::STAGES);
+  const uint32_t tmem_slot = ptx::smem_u32(&tmem_slot_var);
+  volatile uint32_t* tmem_slot_ptr = &tmem_slot_var;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int m_tile = blockIdx.x;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int b = m_tile / tiles_per_img;
+  m_tile -= b * tiles_per_img;
+  const int h0 = (m_tile / p.tiles_w) * p.TH;
+  const int w0 = (m_tile % p.tiles_w) * p.TW;
+  const int n0 = blockIdx.y * BN;
+
+  const int nkb_main = p.ntaps * p.nchunk_main;
+  const int nkb = nkb_main + p.nchunk_sc;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmX);
+    ptx::prefetch_tensormap(&tmW);
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sA_hi = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t sA_lo = sA_hi + A_BYTES;
+        const uint32_t sB_hi = sA_lo + A_BYTES;
+        const uint32_t sB_lo = sB_hi + C::B_BYTES;
+        ptx::mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+        if (kb < nkb_main) {
+          const int tap = kb / p.nchunk_main;
+          const int ch = kb - tap * p.nchunk_main;
+          int dy = 0, dx = 0;
+          if (p.ntaps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+          ptx::tma_load_5d(&tmA, full_bar(stage), sA_hi, ch * BK, w0 + dx, h0 + dy, b, 0);
+          ptx::tma_load_5d(&tmA, full_bar(stage), sA_lo, ch * BK, w0 + dx, h0 + dy, b, 1);
+        } else {
+          const int ch = kb - nkb_main;
+          ptx::tma_load_5d(&tmX, full_bar(stage), sA_hi, ch * BK, w0, h0, b, 0);
+          ptx::tma_load_5d(&tmX, full_bar(stage), sA_lo, ch * BK, w0, h0, b, 1);
+        }
+        ptx::tma_load_3d(&tmW, full_bar(stage), sB_hi, kb * BK, n0, 0);
+        ptx::tma_load_3d(&tmW, full_bar(stage), sB_lo, kb * BK, n0, 1);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(full_bar(stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t sA_hi = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t sA_lo = sA_hi + A_BYTES;
+        const uint32_t sB_hi = sA_lo + A_BYTES;
+        const uint32_t sB_lo = sB_hi + C::B_BYTES;
+        const uint64_t dA_hi = ptx::make_smem_desc_sw128(sA_hi);
+        const uint64_t dA_lo = ptx::make_smem_desc_sw128(sA_lo);
+        const uint64_t dB_hi = ptx::make_smem_desc_sw128(sB_hi);
+        const uint64_t dB_lo = ptx::make_smem_desc_sw128(sB_lo);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);   // 32 B per K step
+          ptx::mma_f16_ss(tmem_acc, dA_hi + koff, dB_hi + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          ptx::mma_f16_ss(tmem_acc, dA_hi + koff, dB_lo + koff, idesc, 1u);
+          ptx::mma_f16_ss(tmem_acc, dA_lo + koff, dB_hi + koff, idesc, 1u);
+        }
+        ptx::mma_commit(empty_bar(stage));          // frees the smem stage when these MMAs retire
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+      ptx::mma_commit(tmem_full_bar);               // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int th = row / p.TW;
+    const int tw = row - th * p.TW;
+    const int h = h0 + th, w = w0 + tw;
+    const bool valid = (h < p.H) && (w < p.W);
+    const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
+    float* orow = p.out + pix * p.ldc;
+    const float* rrow = p.residual ? p.residual + pix * p.ldc : nullptr;
+    const float* brow = p.bias + static_cast<size_t>(b) * p.bias_bstride;
+
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+
+    constexpr int CH = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += CH) {
+      uint32_t r[CH];
+      const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
+      if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(taddr, r);
+      else ptx::tmem_ld_32x32b_x16(taddr, r);
+      ptx::tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+          const int n = n0 + c0 + j;
+          if (n < p.Cout) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(brow + n));
+            float4 v;
+            v.x = __uint_as_float(r[j + 0]) * p.wscale_inv + bv.x;
+            v.y = __uint_as_float(r[j + 1]) * p.wscale_inv + bv.y;
+            v.z = __uint_as_float(r[j + 2]) * p.wscale_inv + bv.z;
+            v.w = __uint_as_float(r[j + 3]) * p.wscale_inv + bv.w;
+            if (rrow) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + n));
+              v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+            }
+            if (p.div_sqrt2) {
+              v.x = __fdiv_rn(v.x, kSqrt2); v.y = __fdiv_rn(v.y, kSqrt2);
+              v.z = __fdiv_rn(v.z, kSqrt2); v.w = __fdiv_rn(v.w, kSqrt2);
+            }
+            *reinterpret_cast<float4*>(orow + n) = v;
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_acc, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Debug / cross-check kernel: same operands, plain fp32 SIMT loops.
+// ------------------------------------------------------------------------------------------------
+__global__ void conv_gemm_simt_kernel(const __half* __restrict__ A, const __half* __restrict__ X,
+                                      const __half* __restrict__ Wp, int Cin, int Cin2, int ntaps, int Npad, int K,
+                                      GemmParams p, int B) {
+  const size_t planeA = static_cast<size_t>(B) * p.H * p.W * Cin;
+  const size_t planeX = static_cast<size_t>(B) * p.H * p.W * Cin2;
+  const size_t planeW = static_cast<size_t>(Npad) * K;
+  const int n = blockIdx.y * blockDim.x + threadIdx.x;
+  const size_t pix = blockIdx.x;
+  const int b = pix / (static_cast<size_t>(p.H) * p.W);
+  const int hw = pix - static_cast<size_t>(b) * p.H * p.W;
+  const int h = hw / p.W, w = hw % p.W;
+  if (n >= p.Cout) return;
+  const __half* wh = Wp + static_cast<size_t>(n) * K;
+  const __half* wl = wh + planeW;
+  float acc = 0.f;
+  for (int tap = 0; tap < ntaps; ++tap) {
+    int dy = 0, dx = 0;
+    if (ntaps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+    const int hh = h + dy, ww = w + dx;
+    if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
+    const __half* ah = A + ((static_cast<size_t>(b) * p.H + hh) * p.W + ww) * Cin;
+    const __half* al = ah + planeA;
+    for (int c = 0; c < Cin; ++c) {
+      const float a = __half2float(ah[c]) + __half2float(al[c]);
+      const float wv = __half2float(wh[tap * Cin + c]) + __half2float(wl[tap * Cin + c]);
+      acc = fmaf(a, wv, acc);
+    }
+  }
+  if (Cin2 > 0) {
+    const __half* xh = X + pix * Cin2;
+    const __half* xl = xh + planeX;
+    for (int c = 0; c < Cin2; ++c) {
+      const float a = __half2float(xh[c]) + __half2float(xl[c]);
+      const float wv = __half2float(wh[ntaps * Cin + c]) + __half2float(wl[ntaps * Cin + c]);
+      acc = fmaf(a, wv, acc);
+    }
+  }
+  float v = acc * p.wscale_inv + p.bias[static_cast<size_t>(b) * p.bias_bstride + n];
+  if (p.residual) v += p.residual[pix * p.ldc + n];
+  if (p.div_sqrt2) v = __fdiv_rn(v, kSqrt2);
+  p.out[pix * p.ldc + n] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn(std::string* err) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) {
+    if (err) *err = std::string("cuTensorMapEncodeTiled not available: ") + cudaGetErrorString(e);
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+// activations [2][B][H][W][C] fp16 -> 5-D map, box {64, TW, TH, 1, 1}
+bool make_act_map(CUtensorMap* m, const __half* base, int B, int H, int W, int C, int TW, int TH, std::string* err) {
+  EncodeTiledFn enc = get_encode_fn(err);
+  if (!enc) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 2};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                           (cuuint64_t)B * H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(act B=%d H=%d W=%d C=%d TW=%d TH=%d) failed: %d", B, H, W, C,
+               TW, TH, (int)r);
+      *err = buf;
+    }
+    return false;
+  }
+  return true;
+}
+
+// weights [2][Npad][K] fp16 -> 3-D map, box {64, BN, 1}
+bool make_w_map(CUtensorMap* m, const __half* base, int Npad, int K, int BN, std::string* err) {
+  EncodeTiledFn enc = get_encode_fn(err);
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Npad, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)Npad * K * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(weights Npad=%d K=%d BN=%d) failed: %d", Npad, K, BN, (int)r);
+      *err = buf;
+    }
+    return false;
+  }
+  return true;
+}
+
+void choose_tile(int H, int W, int& TW, int& TH) {
+  long best = LONG_MAX;
+  TW = 128; TH = 1;
+  for (int tw = 128; tw >= 8; tw >>= 1) {
+    const int th = BM / tw;
+    const long area = static_cast<long>((W + tw - 1) / tw) * tw * ((H + th - 1) / th) * th;
+    if (area < best) { best = area; TW = tw; TH = th; }
+  }
+}
+
+GemmParams make_params(const ConvGemmArgs& a) {
+  GemmParams p{};
+  p.H = a.H; p.W = a.W;
+  choose_tile(a.H, a.W, p.TW, p.TH);
+  p.tiles_w = (a.W + p.TW - 1) / p.TW;
+  p.tiles_h = (a.H + p.TH - 1) / p.TH;
+  p.nchunk_main = a.Cin / BK;
+  p.ntaps = a.ntaps;
+  p.nchunk_sc = a.X ? a.Cin2 / BK : 0;
+  p.Cout = a.Cout; p.ldc = a.ldc;
+  p.wscale_inv = a.wscale_inv;
+  p.bias = a.bias; p.bias_bstride = a.bias_bstride;
+  p.residual = a.residual;
+  p.out = a.out;
+  p.div_sqrt2 = a.div_sqrt2;
+  return p;
+}
+
+bool check_args(const ConvGemmArgs& a, std::string* err) {
+  auto fail = [&](const char* m) { if (err) *err = std::string("conv_gemm: ") + m; return false; };
+  if (a.Cin <= 0 || a.Cin % BK) return fail("Cin must be a positive multiple of 64");
+  if (a.X && (a.Cin2 <= 0 || a.Cin2 % BK)) return fail("Cin2 must be a positive multiple of 64");
+  if (a.ntaps != 1 && a.ntaps != 9) return fail("ntaps must be 1 or 9");
+  if (a.Cout % 4 || a.ldc % 4) return fail("Cout and ldc must be multiples of 4");
+  if (a.Cout > a.Npad) return fail("Cout > Npad");
+  if (!a.bias) return fail("bias is required");
+  if (a.B <= 0 || a.H <= 0 || a.W <= 0) return fail("empty problem");
+  return true;
+}
+
+template <int BN>
+int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
+    attr_set = true;
+  }
+  GemmParams p = make_params(a);
+  const int K = a.ntaps * a.Cin + (a.X ? a.Cin2 : 0);
+  CUtensorMap tmA, tmX, tmW;
+  if (!make_act_map(&tmA, a.A, a.B, a.H, a.W, a.Cin, p.TW, p.TH, err)) return 1;
+  if (a.X) { if (!make_act_map(&tmX, a.X, a.B, a.H, a.W, a.Cin2, p.TW, p.TH, err)) return 1; }
+  else tmX = tmA;
+  if (!make_w_map(&tmW, a.Wp, a.Npad, K, BN, err)) return 1;
+  dim3 grid(a.B * p.tiles_w * p.tiles_h, (a.Cout + BN - 1) / BN);
+  conv_gemm_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(tmA, tmX, tmW, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { if (err) *err = std::string("conv_gemm launch: ") + cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+}  // namespace
+
+int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
+  if (!check_args(a, err)) return 1;
+  if (a.Npad % 128 == 0) return launch_bn<128>(a, s, err);
+  if (a.Npad % 16 == 0) return launch_bn<16>(a, s, err);
+  if (err) *err = "conv_gemm: Npad must be a multiple of 16";
+  return 1;
+}
+
+int launch_conv_gemm_simt(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
+  if (!check_args(a, err)) return 1;
+  GemmParams p = make_params(a);
+  const int K = a.ntaps * a.Cin + (a.X ? a.Cin2 : 0);
+  const int threads = std::min(128, ((a.Cout + 31) / 32) * 32);
+  dim3 grid(static_cast<unsigned>(static_cast<size_t>(a.B) * a.H * a.W), (a.Cout + threads - 1) / threads);
+  conv_gemm_simt_kernel<<<grid, threads, 0, s>>>(a.A, a.X, a.Wp, a.Cin, a.X ? a.Cin2 : 0, a.ntaps, a.Npad, K, p, a.B);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { if (err) *err = std::string("conv_gemm_simt launch: ") + cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+// fp32 -> (hi, lo) fp16 pair, host side (round-to-nearest-even both times).
+static inline void split_half_host(float v, __half* hi, __half* lo) {
+  const __half h = __float2half_rn(v);
+  *hi = h;
+  *lo = __float2half_rn(v - __half2float(h));
+}
+
+int pack_conv_weights_host(const float* w_main, int Cout, int Cin, int ntaps, const float* w_sc, int Cin2, int Npad,
+                           __half* out_hi, __half* out_lo) {
+  const int K = ntaps * Cin + (w_sc ? Cin2 : 0);
+  float amax = 0.f;
+  const size_t n_main = static_cast<size_t>(Cout) * Cin * ntaps;
+  for (size_t i = 0; i < n_main; ++i) amax = std::max(amax, std::fabs(w_main[i]));
+  if (w_sc) for (size_t i = 0; i < static_cast<size_t>(Cout) * Cin2; ++i) amax = std::max(amax, std::fabs(w_sc[i]));
+  // scale so that max|w| lands in [2^13, 2^14): hi stays finite, lo parts stay normal down to 2^-14/2^13 of max
+  int e = 0;
+  if (amax > 0.f && std::isfinite(amax)) {
+    int ex;
+    std::frexp(amax, &ex);      // amax = m * 2^ex, m in [0.5, 1)
+    e = 14 - ex;
+  }
+  const float scale = std::ldexp(1.0f, e);
+  std::memset(out_hi, 0, sizeof(__half) * static_cast<size_t>(Npad) * K);
+  std::memset(out_lo, 0, sizeof(__half) * static_cast<size_t>(Npad) * K);
+  for (int n = 0; n < Cout; ++n) {
+    __half* rh = out_hi + static_cast<size_t>(n) * K;
+    __half* rl = out_lo + static_cast<size_t>(n) * K;
+    for (int c = 0; c < Cin; ++c)
+      for (int t = 0; t < ntaps; ++t) {
+        // PyTorch layout [Cout][Cin][kh][kw], tap = kh*3+kw  ->  K index tap*Cin + c
+        const float v = w_main[(static_cast<size_t>(n) * Cin + c) * ntaps + t] * scale;
+        split_half_host(v, rh + t * Cin + c, rl + t * Cin + c);
+      }
+    if (w_sc)
+      for (int c = 0; c < Cin2; ++c) {
+        const float v = w_sc[static_cast<size_t>(n) * Cin2 + c] * scale;
+        split_half_host(v, rh + ntaps * Cin + c, rl + ntaps * Cin + c);
+      }
+  }
+  return e;
+}
+
+}  // namespace flowse

@@ -1,0 +1,135 @@
+// Internal declarations shared by the .cu translation units of libflowse.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+namespace flowse {
+
+constexpr int kGroups = 32;          // GroupNorm groups: min(C/4, 32) == 32 for every C in the net (layerspp.py:219)
+constexpr float kGnEps = 1e-6f;
+constexpr float kSqrt2 = 1.41421356237309504880f;   // np.sqrt(2.) rounded to fp32 (layerspp.py:274)
+
+// ---------------------------------------------------------------------------------------------
+// Element-wise / small kernels (kernels_pointwise.cu)
+// ---------------------------------------------------------------------------------------------
+// x = y + sigma * z  (FLOWMATCHING.prior_sampling, odes.py:93-100); n complex elements.
+void launch_prior(const float2* y, const float2* z, float sigma, float2* x, size_t n, cudaStream_t s);
+// out = x + v * dt (EulerODEsolver.update_fn, odesolvers.py:42-47, dt = -stepsize); n complex elements.
+void launch_euler_update(const float2* x, const float2* v, float dt, float2* out, size_t n, cudaStream_t s);
+// out = a + c * b   (complex a, b; real scalar c) - Heun / midpoint helper.
+void launch_axpy_c(const float2* a, const float2* b, float c, float2* out, size_t n, cudaStream_t s);
+// out = x + c * (v0 + v1)
+void launch_heun_combine(const float2* x, const float2* v0, const float2* v1, float c, float2* out, size_t n,
+                         cudaStream_t s);
+
+// t_dev[0..B) = t; step_dev[0] = step (scalars passed as kernel arguments)
+void launch_set_scalars(float* t_dev, int B, float t, float* step_dev, float step, cudaStream_t s);
+
+struct TembWeights {
+  const float* fourier_W;   // [128]
+  const float* l1_w;        // [512][256]
+  const float* l1_b;        // [512]
+  const float* l2_w;        // [512][512]
+  const float* l2_b;        // [512]
+  const float* dense_w;     // [R][512]  all Dense_0 stacked
+  const float* dense_b;     // [R]       Dense_0.bias + Conv_0.bias
+  int R;
+};
+// temb_act[b][512] = SiLU(temb(t[b])); bias_table[b][R] = dense_b + dense_w . temb_act[b]
+void launch_temb(const TembWeights& w, const float* t, int B, float* temb_act, float* bias_table, cudaStream_t s);
+
+// conv3x3 4->128 on (x.re, x.im, y.re, y.im) (ncsnpp.py:253-254,285); also writes the 4-plane input pyramid.
+void launch_conv_in(const float2* x, const float2* y, const float* w /*[128][4][3][3]*/, const float* bias,
+                    float* out /*[B,H,W,128]*/, float4* pyr /*[B,H,W,4]*/, int B, int H, int W, cudaStream_t s);
+// 4-channel FIR downsample x2 of the input pyramid (ncsnpp.py:310): [B,2H,2W,4] -> [B,H,W,4]
+void launch_fir_down4(const float4* in, float4* out, int B, int H, int W, cudaStream_t s);
+// Combine(method='sum') (layerspp.py:52-57): out = h + conv1x1(4->C)(pyr) + b
+void launch_combine(const float* h, const float4* pyr, const float* w /*[C][4]*/, const float* b, float* out,
+                    int B, int H, int W, int C, cudaStream_t s);
+// pyramid = FIR-up(prev) + head (ncsnpp.py:357-363). prev may be null (deepest level). head ld = 4.
+void launch_pyr_accum(const float4* prev /*[B,H/2,W/2,4]*/, const float4* head, float4* out, int B, int H, int W,
+                      cudaStream_t s);
+// d = output_layer(pyr / t) (ncsnpp.py:398-403).
+//   mode 0: out = d                         (NCSNpp.forward result)
+//   mode 1: out = -d                        (VFModel.forward result, model.py:164-170)
+//   mode 2: out = xin + stepsize * d        (fused Euler update: x + (-d) * (-stepsize))
+void launch_final(const float4* pyr, const float* t /*[B]*/, const float* wo /*[2][4]*/, const float* bo /*[2]*/,
+                  const float2* xin, const float* stepsize_dev, float2* out, int mode, int B, int HW, cudaStream_t s);
+// row softmax in place, rows x cols fp32
+void launch_softmax_rows(float* s, int rows, int cols, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm statistics + operand preparation (kernels_gn.cu)
+// ---------------------------------------------------------------------------------------------
+// stats[b][g] = {sum, sumsq} (double) over the channel-concatenation of src1 (C1 ch) and src2 (C2 ch, may be null).
+// stats must be zeroed before the call.
+void launch_gn_stats(const float* src1, int C1, const float* src2, int C2, int B, int npix, double* stats,
+                     cudaStream_t s);
+
+enum PrepMode { kPrepPlain = 0, kPrepDown = 1, kPrepUp = 2 };
+struct PrepArgs {
+  const float* src1; int C1;
+  const float* src2; int C2;      // virtual concat [src1, src2] on the channel axis
+  const double* stats;            // [B][32][2]
+  const float* gamma; const float* beta;
+  int B, H, W;                    // INPUT resolution
+  int mode;                       // PrepMode: output resolution is H/2 (down), 2H (up)
+  int silu;                       // apply SiLU after the affine normalisation
+  __half* outA;                   // [2][B][Ho][Wo][C] fp16 hi/lo split of act(GN(x)) (may be null)
+  __half* outX;                   // [2][B][Ho][Wo][C] fp16 hi/lo split of (resampled) raw x (may be null)
+  float* outF;                    // [B][Ho][Wo][C] fp32 act(GN(x)) (may be null)
+  float* outXF;                   // [B][Ho][Wo][C] fp32 resampled raw x (may be null)
+};
+void launch_gn_prep(const PrepArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution on tcgen05 (conv_gemm.cu)
+// ---------------------------------------------------------------------------------------------
+struct ConvGemmArgs {
+  const __half* A;      // [2][B][H][W][Cin]  hi/lo split activations
+  int Cin;              // multiple of 64
+  int ntaps;            // 9 (3x3, pad 1) or 1 (1x1)
+  const __half* X;      // optional shortcut operand [2][B][H][W][Cin2] (extra 1x1 K-blocks), may be null
+  int Cin2;             // multiple of 64 or 0
+  const __half* Wp;     // [2][Npad][K] hi/lo split packed weights, K = ntaps*Cin + Cin2, scaled by 2^wexp
+  int Npad;             // rows of Wp (multiple of the N tile)
+  float wscale_inv;     // 2^-wexp
+  const float* bias;    // [bias_bstride ? B : 1][Cout]
+  int bias_bstride;     // 0 or stride (floats) between batch elements
+  const float* residual;// optional fp32 [B][H][W][ldc]
+  int div_sqrt2;        // divide the result by sqrt(2) (skip_rescale)
+  float* out;           // fp32 [B][H][W][ldc]
+  int Cout;             // valid output channels (<= Npad)
+  int ldc;
+  int B, H, W;
+};
+// returns 0 on success; fills err otherwise.
+int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t s, std::string* err);
+// Slow SIMT evaluation of exactly the same operands (debug / cross-check only; never on the product path).
+int launch_conv_gemm_simt(const ConvGemmArgs& a, cudaStream_t s, std::string* err);
+// Host-side packing: fp32 [Cout][Cin][kh][kw] (+ optional 1x1 shortcut [Cout][Cin2]) -> K-major fp16 hi/lo.
+// out_hi/out_lo: [Npad][K]; returns the power-of-two exponent used.
+int pack_conv_weights_host(const float* w_main, int Cout, int Cin, int ntaps, const float* w_sc, int Cin2,
+                           int Npad, __half* out_hi, __half* out_lo);
+
+// ---------------------------------------------------------------------------------------------
+// fp32 SIMT GEMM for the attention blocks (sgemm.cu)
+// ---------------------------------------------------------------------------------------------
+struct SgemmArgs {
+  const float* A; int lda; long long strideA;      // [M][K] row-major
+  const float* Bm; int ldb; long long strideB;     // transB ? [N][K] : [K][N]
+  int transB;
+  float* C; int ldc; long long strideC;
+  int M, N, K, batch;
+  float alpha;                                     // applied to the accumulated product
+  const float* bias;                               // [N] or null
+  const float* residual; int ldr; long long strideR;   // optional, added after bias
+  int div_sqrt2;
+  __half* split_out;                               // optional: also not used (reserved)
+};
+void launch_sgemm(const SgemmArgs& a, cudaStream_t s);
+
+}  // namespace flowse

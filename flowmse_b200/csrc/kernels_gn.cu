@@ -1,0 +1,230 @@
+// GroupNorm statistics and the fused operand-preparation kernel.
+//
+// Reference semantics: nn.GroupNorm(32, C, eps=1e-6) followed by SiLU, optionally followed by the StyleGAN2 FIR
+// resampling of BOTH the activated tensor h and the raw input x
+// (/root/reference/flowmse/backbones/ncsnpp_utils/layerspp.py:243-258; FIR closed forms: up_or_down_sampling.py:195-257,
+// SURVEY.md Appendix B).  The reference runs these as 3-6 separate full-tensor passes; here ONE HBM-bound pass reads x
+// once and writes the conv operands directly in the fp16 hi/lo split format the tcgen05 GEMM consumes.
+#include "flowse_internal.h"
+
+namespace flowse {
+
+namespace {
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+
+__device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+
+// exact hi/lo split: v ~= hi + lo with hi, lo fp16 (v saturated to the fp16 range first)
+__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
+  const float a = clamp_h(v.x), b = clamp_h(v.y), c = clamp_h(v.z), d = clamp_h(v.w);
+  const __half ha = __float2half_rn(a), hb = __float2half_rn(b), hc = __float2half_rn(c), hd = __float2half_rn(d);
+  const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
+  const __half lc = __float2half_rn(c - __half2float(hc)), ld = __float2half_rn(d - __half2float(hd));
+  __half2 h01 = __halves2half2(ha, hb), h23 = __halves2half2(hc, hd);
+  __half2 l01 = __halves2half2(la, lb), l23 = __halves2half2(lc, ld);
+  hi.x = *reinterpret_cast<uint32_t*>(&h01); hi.y = *reinterpret_cast<uint32_t*>(&h23);
+  lo.x = *reinterpret_cast<uint32_t*>(&l01); lo.y = *reinterpret_cast<uint32_t*>(&l23);
+}
+
+// ---------------------------------------------------------------------------------------------
+// statistics: per (batch, group) sum and sum of squares, accumulated in double
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ s1, int C1, const float* __restrict__ s2, int C2, int npix, int chunk,
+                double* __restrict__ stats) {
+  const int C = C1 + C2;
+  const int cvec = C >> 2;                 // float4 per pixel
+  const int ppi = blockDim.x / cvec;       // pixels per iteration
+  const int b = blockIdx.y;
+  __shared__ float gs[kGroups], gq[kGroups];
+  if (threadIdx.x < kGroups) { gs[threadIdx.x] = 0.f; gq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int v = threadIdx.x % cvec;
+  const int pp = threadIdx.x / cvec;
+  if (pp < ppi) {
+    const int c = v << 2;
+    const float* src;
+    int ld, cc;
+    if (c < C1) { src = s1; ld = C1; cc = c; } else { src = s2; ld = C2; cc = c - C1; }
+    const int p0 = blockIdx.x * chunk;
+    const int p1 = min(npix, p0 + chunk);
+    float s = 0.f, q = 0.f;
+    for (int p = p0 + pp; p < p1; p += ppi) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(src + (static_cast<size_t>(b) * npix + p) * ld + cc));
+      s += (x.x + x.y) + (x.z + x.w);
+      q += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+    }
+    const int g = c / (C / kGroups);
+    atomicAdd(&gs[g], s);
+    atomicAdd(&gq[g], q);
+  }
+  __syncthreads();
+  if (threadIdx.x < kGroups) {
+    atomicAdd(&stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 0], static_cast<double>(gs[threadIdx.x]));
+    atomicAdd(&stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 1], static_cast<double>(gq[threadIdx.x]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep: y = act(GN(x)) (+ FIR), split to fp16 hi/lo; optional raw-x split for the 1x1 shortcut
+// ---------------------------------------------------------------------------------------------
+struct PrepK {
+  const float* s1; int C1;
+  const float* s2; int C2;
+  const double* stats;
+  const float* gamma; const float* beta;
+  int H, W, Ho, Wo, mode, silu, B;
+  __half* outA; __half* outX; float* outF; float* outXF;
+};
+
+__device__ __forceinline__ float4 load_src(const PrepK& k, int b, int h, int w, int c) {
+  const size_t pix = (static_cast<size_t>(b) * k.H + h) * k.W + w;
+  if (c < k.C1) return __ldg(reinterpret_cast<const float4*>(k.s1 + pix * k.C1 + c));
+  return __ldg(reinterpret_cast<const float4*>(k.s2 + pix * k.C2 + (c - k.C1)));
+}
+
+__device__ __forceinline__ float4 norm_act(const float4 x, const float4 sc, const float4 sh, int silu) {
+  float4 y;
+  y.x = fmaf(x.x, sc.x, sh.x); y.y = fmaf(x.y, sc.y, sh.y);
+  y.z = fmaf(x.z, sc.z, sh.z); y.w = fmaf(x.w, sc.w, sh.w);
+  if (silu) { y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w); }
+  return y;
+}
+
+__device__ __forceinline__ void fma4(float4& acc, float wgt, const float4 v) {
+  acc.x = fmaf(wgt, v.x, acc.x); acc.y = fmaf(wgt, v.y, acc.y);
+  acc.z = fmaf(wgt, v.z, acc.z); acc.w = fmaf(wgt, v.w, acc.w);
+}
+
+__global__ void __launch_bounds__(256)
+gn_prep_kernel(const PrepK k) {
+  const int C = k.C1 + k.C2;
+  const int cvec = C >> 2;
+  const int b = blockIdx.y;
+  __shared__ float s_mean[kGroups], s_rstd[kGroups];
+  if (threadIdx.x < kGroups) {
+    const double n = static_cast<double>(k.H) * k.W * (C / kGroups);
+    const double su = k.stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 0];
+    const double sq = k.stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 1];
+    const double mean = su / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
+  }
+  __syncthreads();
+  const size_t total = static_cast<size_t>(k.Ho) * k.Wo * cvec;
+  const size_t plane = static_cast<size_t>(k.B) * k.Ho * k.Wo * C;
+  for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = idx % cvec;
+    const size_t opix = idx / cvec;
+    const int wo = opix % k.Wo;
+    const int ho = opix / k.Wo;
+    const int c = v << 2;
+    const int g = c / (C / kGroups);
+    const float mean = s_mean[g], rstd = s_rstd[g];
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(k.gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(k.beta + c));
+    float4 sc, sh;   // y = x*sc + sh  with sc = rstd*gamma, sh = beta - mean*sc
+    sc.x = rstd * ga.x; sc.y = rstd * ga.y; sc.z = rstd * ga.z; sc.w = rstd * ga.w;
+    sh.x = fmaf(-mean, sc.x, be.x); sh.y = fmaf(-mean, sc.y, be.y);
+    sh.z = fmaf(-mean, sc.z, be.z); sh.w = fmaf(-mean, sc.w, be.w);
+
+    float4 ya, xa;
+    if (k.mode == kPrepPlain) {
+      xa = load_src(k, b, ho, wo, c);
+      ya = norm_act(xa, sc, sh, k.silu);
+    } else if (k.mode == kPrepDown) {
+      // out[m] = (x[2m-1] + 3x[2m] + 3x[2m+1] + x[2m+2]) / 8 per axis; 2-D taps outer([1,3,3,1])/64
+      ya = make_float4(0.f, 0.f, 0.f, 0.f); xa = ya;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int hi = 2 * ho - 1 + i;
+        if (hi < 0 || hi >= k.H) continue;
+        const float wi_ = (i == 0 || i == 3) ? 1.f : 3.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int wj = 2 * wo - 1 + j;
+          if (wj < 0 || wj >= k.W) continue;
+          const float wgt = wi_ * ((j == 0 || j == 3) ? 1.f : 3.f) * (1.f / 64.f);
+          const float4 x = load_src(k, b, hi, wj, c);
+          fma4(xa, wgt, x);
+          fma4(ya, wgt, norm_act(x, sc, sh, k.silu));
+        }
+      }
+    } else {
+      // up x2: out[2m] = .25 x[m-1] + .75 x[m];  out[2m+1] = .75 x[m] + .25 x[m+1]; 2-D taps {1,3,3,9}/16
+      ya = make_float4(0.f, 0.f, 0.f, 0.f); xa = ya;
+      const int mh = ho >> 1, mw = wo >> 1;
+      const int h_a = (ho & 1) ? mh : mh - 1, h_b = (ho & 1) ? mh + 1 : mh;      // weights: a,b
+      const float wha = (ho & 1) ? 3.f : 1.f, whb = (ho & 1) ? 1.f : 3.f;
+      const int w_a = (wo & 1) ? mw : mw - 1, w_b = (wo & 1) ? mw + 1 : mw;
+      const float wwa = (wo & 1) ? 3.f : 1.f, wwb = (wo & 1) ? 1.f : 3.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int hi = i ? h_b : h_a;
+        if (hi < 0 || hi >= k.H) continue;
+        const float wi_ = i ? whb : wha;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int wj = j ? w_b : w_a;
+          if (wj < 0 || wj >= k.W) continue;
+          const float wgt = wi_ * (j ? wwb : wwa) * (1.f / 16.f);
+          const float4 x = load_src(k, b, hi, wj, c);
+          fma4(xa, wgt, x);
+          fma4(ya, wgt, norm_act(x, sc, sh, k.silu));
+        }
+      }
+    }
+    const size_t o = (static_cast<size_t>(b) * k.Ho * k.Wo + opix) * C + c;
+    if (k.outA) {
+      uint2 hi, lo;
+      split4(ya, hi, lo);
+      *reinterpret_cast<uint2*>(k.outA + o) = hi;
+      *reinterpret_cast<uint2*>(k.outA + plane + o) = lo;
+    }
+    if (k.outX) {
+      uint2 hi, lo;
+      split4(xa, hi, lo);
+      *reinterpret_cast<uint2*>(k.outX + o) = hi;
+      *reinterpret_cast<uint2*>(k.outX + plane + o) = lo;
+    }
+    if (k.outF) *reinterpret_cast<float4*>(k.outF + o) = ya;
+    if (k.outXF) *reinterpret_cast<float4*>(k.outXF + o) = xa;
+  }
+}
+
+}  // namespace
+
+void launch_gn_stats(const float* src1, int C1, const float* src2, int C2, int B, int npix, double* stats,
+                     cudaStream_t s) {
+  const int C = C1 + (src2 ? C2 : 0);
+  const int cvec = C / 4;
+  const int ppi = 256 / cvec;
+  int target_blocks = std::max(1, 592 / B);
+  int chunk = (npix + target_blocks - 1) / target_blocks;
+  chunk = ((chunk + ppi - 1) / ppi) * ppi;
+  if (chunk < ppi * 4) chunk = ppi * 4;
+  dim3 grid((npix + chunk - 1) / chunk, B);
+  gn_stats_kernel<<<grid, 256, 0, s>>>(src1, C1, src2, src2 ? C2 : 0, npix, chunk, stats);
+}
+
+void launch_gn_prep(const PrepArgs& a, cudaStream_t s) {
+  PrepK k;
+  k.s1 = a.src1; k.C1 = a.C1; k.s2 = a.src2; k.C2 = a.src2 ? a.C2 : 0;
+  k.stats = a.stats; k.gamma = a.gamma; k.beta = a.beta;
+  k.H = a.H; k.W = a.W; k.mode = a.mode; k.silu = a.silu; k.B = a.B;
+  k.Ho = a.mode == kPrepDown ? a.H / 2 : (a.mode == kPrepUp ? a.H * 2 : a.H);
+  k.Wo = a.mode == kPrepDown ? a.W / 2 : (a.mode == kPrepUp ? a.W * 2 : a.W);
+  k.outA = a.outA; k.outX = a.outX; k.outF = a.outF; k.outXF = a.outXF;
+  const size_t total = static_cast<size_t>(k.Ho) * k.Wo * ((k.C1 + k.C2) / 4);
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = 148 * 16;
+  if (blocks > cap) blocks = cap;
+  dim3 grid(static_cast<unsigned>(blocks), a.B);
+  gn_prep_kernel<<<grid, 256, 0, s>>>(k);
+}
+
+}  // namespace flowse

@@ -1,0 +1,407 @@
+// HBM-bound element-wise kernels of the sampler plus the small 4-channel "pyramid" kernels of NCSN++.
+// Each cites the reference line it replaces (paths relative to /root/reference).
+#include "flowse_internal.h"
+
+namespace flowse {
+
+namespace {
+
+constexpr float kPiF = 3.14159274101257324219f;   // np.pi rounded to fp32 (scalar * fp32 tensor, layerspp.py:40)
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+// a*b + c with two roundings (no FMA contraction): bit-identical to torch's separate mul and add
+__device__ __forceinline__ float madd(float a, float b, float c) { return __fadd_rn(__fmul_rn(a, b), c); }
+
+// ------------------------------------------------------------------------------------------------
+// Sampler element-wise updates.  complex64 is handled as float2 pairs; two complex per thread (float4).
+// ------------------------------------------------------------------------------------------------
+// x = y + sigma * z                                   (flowmse/odes.py:93-100)
+__global__ void __launch_bounds__(256)
+prior_kernel(const float4* __restrict__ y, const float4* __restrict__ z, float sigma, float4* __restrict__ x,
+             size_t n4, const float2* y2, const float2* z2, float2* x2, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = __ldg(y + i), b = __ldg(z + i);
+    // complex * real-tensor std: (z.re*s - z.im*0, z.re*0 + z.im*s) == (z.re*s, z.im*s) for finite z
+    x[i] = make_float4(madd(b.x, sigma, a.x), madd(b.y, sigma, a.y), madd(b.z, sigma, a.z), madd(b.w, sigma, a.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) {
+    const float2 a = y2[n - 1], b = z2[n - 1];
+    x2[n - 1] = make_float2(madd(b.x, sigma, a.x), madd(b.y, sigma, a.y));
+  }
+}
+
+// out = a + c * b                                     (flowmse/sampling/odesolvers.py:42-47 with c = dt)
+__global__ void __launch_bounds__(256)
+axpy_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float c, float4* __restrict__ out, size_t n4,
+            const float2* a2, const float2* b2, float2* o2, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 u = __ldg(a + i), v = __ldg(b + i);
+    out[i] = make_float4(madd(v.x, c, u.x), madd(v.y, c, u.y), madd(v.z, c, u.z), madd(v.w, c, u.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) {
+    const float2 u = a2[n - 1], v = b2[n - 1];
+    o2[n - 1] = make_float2(madd(v.x, c, u.x), madd(v.y, c, u.y));
+  }
+}
+
+// out = x + c * (v0 + v1)                             (Heun corrector)
+__global__ void __launch_bounds__(256)
+heun_kernel(const float2* __restrict__ x, const float2* __restrict__ v0, const float2* __restrict__ v1, float c,
+            float2* __restrict__ out, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float2 a = x[i], p = v0[i], q = v1[i];
+    out[i] = make_float2(madd(c, __fadd_rn(p.x, q.x), a.x), madd(c, __fadd_rn(p.y, q.y), a.y));
+  }
+}
+
+__global__ void set_scalars_kernel(float* t_dev, int B, float t, float* step_dev, float step) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) t_dev[i] = t;
+  if (i == 0) step_dev[0] = step;
+}
+
+inline unsigned grid_for(size_t n, int per_block = 256, unsigned cap = 148 * 8) {
+  size_t b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  return static_cast<unsigned>(b > cap ? cap : b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Time embedding (layerspp.py:39-41, ncsnpp.py:259,271-275) and all 49 Dense_0 biases (layerspp.py:262-263)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+temb_mlp_kernel(const TembWeights w, const float* __restrict__ t, float* __restrict__ temb_act) {
+  __shared__ float emb[256];
+  __shared__ float h1[512];
+  const int b = blockIdx.x;
+  const int j = threadIdx.x;
+  if (j < 128) {
+    const float lx = logf(t[b]);
+    const float xp = ((lx * w.fourier_W[j]) * 2.0f) * kPiF;   // same fp32 op order as the reference
+    emb[j] = sinf(xp);
+    emb[128 + j] = cosf(xp);
+  }
+  __syncthreads();
+  {
+    const float* row = w.l1_w + static_cast<size_t>(j) * 256;
+    float acc = 0.f;
+    for (int i = 0; i < 256; ++i) acc = fmaf(row[i], emb[i], acc);
+    h1[j] = silu_f(acc + w.l1_b[j]);
+  }
+  __syncthreads();
+  {
+    const float* row = w.l2_w + static_cast<size_t>(j) * 512;
+    float acc = 0.f;
+    for (int i = 0; i < 512; ++i) acc = fmaf(row[i], h1[i], acc);
+    temb_act[static_cast<size_t>(b) * 512 + j] = silu_f(acc + w.l2_b[j]);   // act(temb), input of every Dense_0
+  }
+}
+
+// one warp per output row r: table[b][r] = dense_b[r] + dense_w[r] . temb_act[b]
+__global__ void __launch_bounds__(256)
+temb_dense_kernel(const float* __restrict__ dw, const float* __restrict__ db, const float* __restrict__ act, int R,
+                  int B, float* __restrict__ table) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  const float4* row = reinterpret_cast<const float4*>(dw + static_cast<size_t>(warp) * 512);
+  float4 wv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) wv[i] = __ldg(row + lane + 32 * i);
+  for (int b = 0; b < B; ++b) {
+    const float4* a = reinterpret_cast<const float4*>(act + static_cast<size_t>(b) * 512);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 x = __ldg(a + lane + 32 * i);
+      acc = fmaf(wv[i].x, x.x, acc); acc = fmaf(wv[i].y, x.y, acc);
+      acc = fmaf(wv[i].z, x.z, acc); acc = fmaf(wv[i].w, x.w, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) table[static_cast<size_t>(b) * R + warp] = acc + db[warp];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Input conv 3x3, 4 -> 128 (ncsnpp.py:253-254,285).  SIMT fp32: K = 36 is too thin for tensor cores.
+// Block = 8 warps, tile 4 rows x 32 cols; warp g owns 16 pixels, lane owns 4 output channels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_in_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const float* __restrict__ wgt,
+               const float* __restrict__ bias, float* __restrict__ out, float4* __restrict__ pyr, int H, int W) {
+  __shared__ float4 s_in[6][34];          // 4 channels per pixel, halo 1
+  __shared__ float4 s_w[9][4][32];        // [tap][ci][lane] -> 4 consecutive output channels
+  const int b = blockIdx.z;
+  const int h0 = blockIdx.y * 4, w0 = blockIdx.x * 32;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 9 * 4 * 32; i += 256) {
+    const int l = i & 31, ci = (i >> 5) & 3, tap = i >> 7;
+    float4 v;
+    // weight layout [128][4][3][3]
+    v.x = wgt[((4 * l + 0) * 4 + ci) * 9 + tap];
+    v.y = wgt[((4 * l + 1) * 4 + ci) * 9 + tap];
+    v.z = wgt[((4 * l + 2) * 4 + ci) * 9 + tap];
+    v.w = wgt[((4 * l + 3) * 4 + ci) * 9 + tap];
+    s_w[tap][ci][l] = v;
+  }
+  for (int i = tid; i < 6 * 34; i += 256) {
+    const int r = i / 34, c = i % 34;
+    const int h = h0 + r - 1, w = w0 + c - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      const size_t p = (static_cast<size_t>(b) * H + h) * W + w;
+      const float2 a = x[p], c2 = y[p];
+      v = make_float4(a.x, a.y, c2.x, c2.y);
+      if (r >= 1 && r <= 4 && c >= 1 && c <= 32) pyr[p] = v;
+    }
+    s_in[r][c] = v;
+  }
+  __syncthreads();
+  const int g = tid >> 5, lane = tid & 31;
+  const int row = g >> 1, col0 = (g & 1) * 16;
+  float4 acc[16];
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + lane);
+#pragma unroll
+  for (int p = 0; p < 16; ++p) acc[p] = bv;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3, dx = tap % 3;
+    const float4 w0v = s_w[tap][0][lane], w1v = s_w[tap][1][lane], w2v = s_w[tap][2][lane], w3v = s_w[tap][3][lane];
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+      const float4 in = s_in[row + dy][col0 + p + dx];
+      acc[p].x = fmaf(in.x, w0v.x, acc[p].x); acc[p].y = fmaf(in.x, w0v.y, acc[p].y);
+      acc[p].z = fmaf(in.x, w0v.z, acc[p].z); acc[p].w = fmaf(in.x, w0v.w, acc[p].w);
+      acc[p].x = fmaf(in.y, w1v.x, acc[p].x); acc[p].y = fmaf(in.y, w1v.y, acc[p].y);
+      acc[p].z = fmaf(in.y, w1v.z, acc[p].z); acc[p].w = fmaf(in.y, w1v.w, acc[p].w);
+      acc[p].x = fmaf(in.z, w2v.x, acc[p].x); acc[p].y = fmaf(in.z, w2v.y, acc[p].y);
+      acc[p].z = fmaf(in.z, w2v.z, acc[p].z); acc[p].w = fmaf(in.z, w2v.w, acc[p].w);
+      acc[p].x = fmaf(in.w, w3v.x, acc[p].x); acc[p].y = fmaf(in.w, w3v.y, acc[p].y);
+      acc[p].z = fmaf(in.w, w3v.z, acc[p].z); acc[p].w = fmaf(in.w, w3v.w, acc[p].w);
+    }
+  }
+  const int h = h0 + row;
+  if (h < H) {
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+      const int w = w0 + col0 + p;
+      if (w < W) {
+        const size_t pix = (static_cast<size_t>(b) * H + h) * W + w;
+        reinterpret_cast<float4*>(out + pix * 128)[lane] = acc[p];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4-channel pyramids (ncsnpp.py:310, 347-366)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fir_down4_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int H, int W) {
+  // in: [B][2H][2W], out: [B][H][W]
+  const size_t total = static_cast<size_t>(B) * H * W;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int w = i % W;
+  const int h = (i / W) % H;
+  const int b = i / (static_cast<size_t>(W) * H);
+  const int Hi = 2 * H, Wi = 2 * W;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int hi = 2 * h - 1 + a;
+    if (hi < 0 || hi >= Hi) continue;
+    const float wa = (a == 0 || a == 3) ? 1.f : 3.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int wi = 2 * w - 1 + c;
+      if (wi < 0 || wi >= Wi) continue;
+      const float wgt = wa * ((c == 0 || c == 3) ? 1.f : 3.f) * (1.f / 64.f);
+      const float4 v = __ldg(in + (static_cast<size_t>(b) * Hi + hi) * Wi + wi);
+      acc.x = fmaf(wgt, v.x, acc.x); acc.y = fmaf(wgt, v.y, acc.y);
+      acc.z = fmaf(wgt, v.z, acc.z); acc.w = fmaf(wgt, v.w, acc.w);
+    }
+  }
+  out[i] = acc;
+}
+
+// out = h + conv1x1(4->C)(pyr) + b                  (Combine 'sum', layerspp.py:52-57)
+__global__ void __launch_bounds__(256)
+combine_kernel(const float* __restrict__ h, const float4* __restrict__ pyr, const float* __restrict__ w,
+               const float* __restrict__ bias, float* __restrict__ out, size_t npix, int C) {
+  const int cvec = C >> 2;
+  const size_t total = npix * cvec;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int v = i % cvec;
+    const size_t pix = i / cvec;
+    const int c = v << 2;
+    const float4 p = __ldg(pyr + pix);
+    const float4 hv = __ldg(reinterpret_cast<const float4*>(h + pix * C + c));
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (c + 0) * 4));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (c + 1) * 4));
+    const float4 w2 = __ldg(reinterpret_cast<const float4*>(w + (c + 2) * 4));
+    const float4 w3 = __ldg(reinterpret_cast<const float4*>(w + (c + 3) * 4));
+    float4 o;
+    o.x = hv.x + (fmaf(w0.w, p.w, fmaf(w0.z, p.z, fmaf(w0.y, p.y, w0.x * p.x))) + bv.x);
+    o.y = hv.y + (fmaf(w1.w, p.w, fmaf(w1.z, p.z, fmaf(w1.y, p.y, w1.x * p.x))) + bv.y);
+    o.z = hv.z + (fmaf(w2.w, p.w, fmaf(w2.z, p.z, fmaf(w2.y, p.y, w2.x * p.x))) + bv.z);
+    o.w = hv.w + (fmaf(w3.w, p.w, fmaf(w3.z, p.z, fmaf(w3.y, p.y, w3.x * p.x))) + bv.w);
+    *reinterpret_cast<float4*>(out + pix * C + c) = o;
+  }
+}
+
+// out = FIR-up(prev) + head                           (ncsnpp.py:357-363)
+__global__ void __launch_bounds__(256)
+pyr_accum_kernel(const float4* __restrict__ prev, const float4* __restrict__ head, float4* __restrict__ out, int B,
+                 int H, int W) {
+  const size_t total = static_cast<size_t>(B) * H * W;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float4 acc = head[i];
+  if (prev) {
+    const int w = i % W;
+    const int h = (i / W) % H;
+    const int b = i / (static_cast<size_t>(W) * H);
+    const int Hp = H >> 1, Wp = W >> 1;
+    const int mh = h >> 1, mw = w >> 1;
+    const int h_a = (h & 1) ? mh : mh - 1, h_b = (h & 1) ? mh + 1 : mh;
+    const float wha = (h & 1) ? 3.f : 1.f, whb = (h & 1) ? 1.f : 3.f;
+    const int w_a = (w & 1) ? mw : mw - 1, w_b = (w & 1) ? mw + 1 : mw;
+    const float wwa = (w & 1) ? 3.f : 1.f, wwb = (w & 1) ? 1.f : 3.f;
+    float4 up = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int hi = a ? h_b : h_a;
+      if (hi < 0 || hi >= Hp) continue;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int wi = c ? w_b : w_a;
+        if (wi < 0 || wi >= Wp) continue;
+        const float wgt = (a ? whb : wha) * (c ? wwb : wwa) * (1.f / 16.f);
+        const float4 v = __ldg(prev + (static_cast<size_t>(b) * Hp + hi) * Wp + wi);
+        up.x = fmaf(wgt, v.x, up.x); up.y = fmaf(wgt, v.y, up.y);
+        up.z = fmaf(wgt, v.z, up.z); up.w = fmaf(wgt, v.w, up.w);
+      }
+    }
+    acc.x = up.x + acc.x; acc.y = up.y + acc.y; acc.z = up.z + acc.z; acc.w = up.w + acc.w;
+  }
+  out[i] = acc;
+}
+
+// d = output_layer(pyr / t); see launch_final for the modes
+__global__ void __launch_bounds__(256)
+final_kernel(const float4* __restrict__ pyr, const float* __restrict__ t, const float* __restrict__ wo,
+             const float* __restrict__ bo, const float2* __restrict__ xin, const float* __restrict__ step_dev,
+             float2* __restrict__ out, int mode, int B, int HW) {
+  const size_t total = static_cast<size_t>(B) * HW;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const float w00 = wo[0], w01 = wo[1], w02 = wo[2], w03 = wo[3];
+  const float w10 = wo[4], w11 = wo[5], w12 = wo[6], w13 = wo[7];
+  const float b0 = bo[0], b1 = bo[1];
+  const float step = (mode == 2) ? step_dev[0] : 0.f;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int b = i / HW;
+    const float tb = t[b];
+    float4 p = __ldg(pyr + i);
+    p.x = __fdiv_rn(p.x, tb); p.y = __fdiv_rn(p.y, tb); p.z = __fdiv_rn(p.z, tb); p.w = __fdiv_rn(p.w, tb);
+    const float dre = fmaf(w03, p.w, fmaf(w02, p.z, fmaf(w01, p.y, w00 * p.x))) + b0;
+    const float dim = fmaf(w13, p.w, fmaf(w12, p.z, fmaf(w11, p.y, w10 * p.x))) + b1;
+    float2 o;
+    if (mode == 0) o = make_float2(dre, dim);
+    else if (mode == 1) o = make_float2(-dre, -dim);
+    else { const float2 xv = xin[i]; o = make_float2(madd(step, dre, xv.x), madd(step, dim, xv.y)); }
+    out[i] = o;
+  }
+}
+
+// row softmax, one warp per row                        (layerspp.py:84)
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(float* __restrict__ s, int rows, int cols) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* r = s + static_cast<size_t>(row) * cols;
+  float m = -INFINITY;
+  for (int i = lane; i < cols; i += 32) m = fmaxf(m, r[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int i = lane; i < cols; i += 32) { const float e = expf(r[i] - m); r[i] = e; sum += e; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int i = lane; i < cols; i += 32) r[i] = __fdiv_rn(r[i], sum);
+}
+
+}  // namespace
+
+void launch_set_scalars(float* t_dev, int B, float t, float* step_dev, float step, cudaStream_t s) {
+  set_scalars_kernel<<<(B + 127) / 128, 128, 0, s>>>(t_dev, B, t, step_dev, step);
+}
+
+void launch_prior(const float2* y, const float2* z, float sigma, float2* x, size_t n, cudaStream_t s) {
+  const size_t n4 = n / 2;
+  prior_kernel<<<grid_for(n4), 256, 0, s>>>(reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(z),
+                                            sigma, reinterpret_cast<float4*>(x), n4, y, z, x, n);
+}
+
+void launch_axpy_c(const float2* a, const float2* b, float c, float2* out, size_t n, cudaStream_t s) {
+  const size_t n4 = n / 2;
+  axpy_kernel<<<grid_for(n4), 256, 0, s>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), c,
+                                           reinterpret_cast<float4*>(out), n4, a, b, out, n);
+}
+
+void launch_euler_update(const float2* x, const float2* v, float dt, float2* out, size_t n, cudaStream_t s) {
+  launch_axpy_c(x, v, dt, out, n, s);
+}
+
+void launch_heun_combine(const float2* x, const float2* v0, const float2* v1, float c, float2* out, size_t n,
+                         cudaStream_t s) {
+  heun_kernel<<<grid_for(n), 256, 0, s>>>(x, v0, v1, c, out, n);
+}
+
+void launch_temb(const TembWeights& w, const float* t, int B, float* temb_act, float* bias_table, cudaStream_t s) {
+  temb_mlp_kernel<<<B, 512, 0, s>>>(w, t, temb_act);
+  const int warps_per_block = 8;
+  temb_dense_kernel<<<(w.R + warps_per_block - 1) / warps_per_block, 256, 0, s>>>(w.dense_w, w.dense_b, temb_act, w.R,
+                                                                                  B, bias_table);
+}
+
+void launch_conv_in(const float2* x, const float2* y, const float* w, const float* bias, float* out, float4* pyr,
+                    int B, int H, int W, cudaStream_t s) {
+  dim3 grid((W + 31) / 32, (H + 3) / 4, B);
+  conv_in_kernel<<<grid, 256, 0, s>>>(x, y, w, bias, out, pyr, H, W);
+}
+
+void launch_fir_down4(const float4* in, float4* out, int B, int H, int W, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * H * W;
+  fir_down4_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out, B, H, W);
+}
+
+void launch_combine(const float* h, const float4* pyr, const float* w, const float* b, float* out, int B, int H,
+                    int W, int C, cudaStream_t s) {
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  combine_kernel<<<grid_for(npix * (C / 4)), 256, 0, s>>>(h, pyr, w, b, out, npix, C);
+}
+
+void launch_pyr_accum(const float4* prev, const float4* head, float4* out, int B, int H, int W, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * H * W;
+  pyr_accum_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(prev, head, out, B, H, W);
+}
+
+void launch_final(const float4* pyr, const float* t, const float* wo, const float* bo, const float2* xin,
+                  const float* stepsize_dev, float2* out, int mode, int B, int HW, cudaStream_t s) {
+  final_kernel<<<grid_for(static_cast<size_t>(B) * HW), 256, 0, s>>>(pyr, t, wo, bo, xin, stepsize_dev, out, mode, B,
+                                                                      HW);
+}
+
+void launch_softmax_rows(float* sm, int rows, int cols, cudaStream_t st) {
+  softmax_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(sm, rows, cols);
+}
+
+}  // namespace flowse

@@ -1,0 +1,112 @@
+/* libflowse - C ABI of the B200-native FlowSE reverse-ODE sampling hot path.
+ *
+ * Every entry point replaces a piece of the reference's Python hot path (paths relative to the seongq/flowmse
+ * checkout, /root/reference).  The reference has no FFI for this path (it is pure PyTorch plus one JIT-built torch
+ * extension), so the binding a maintainer adds is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - complex64 tensors are passed as pointers to interleaved (re, im) fp32 pairs, layout [B,1,F=256,T] contiguous
+ *     (the reference's NCHW layout with C=1), T % 64 == 0 (flowmse/util/other.py:83-90).
+ *   - All data pointers are DEVICE pointers owned by the caller unless a parameter says "host".
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no hidden synchronisation
+ *     (except flowse_load_weights and the first call for a new (B,T), which allocate).
+ *   - Return value 0 = ok; otherwise an error code, message via flowse_last_error().  There is no CPU fallback.
+ *   - One context per (process, device); a context is not re-entrant.
+ */
+#ifndef FLOWSE_H
+#define FLOWSE_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct flowse_ctx flowse_ctx;
+
+/* One tensor of the backbone state_dict inside a flat fp32 blob (reference names, e.g.
+ * "all_modules.4.Conv_0.weight"; flowmse/backbones/ncsnpp.py:99-245). */
+typedef struct {
+  char name[96];
+  long long offset; /* in floats from the start of the blob */
+  long long numel;
+} flowse_tensor_desc;
+
+enum { FLOWSE_SOLVER_EULER = 0, FLOWSE_SOLVER_HEUN = 1, FLOWSE_SOLVER_MIDPOINT = 2 };
+
+/* Context life cycle.  `device` is a CUDA ordinal. */
+int flowse_create(flowse_ctx** out, int device);
+void flowse_destroy(flowse_ctx* ctx);
+/* Last error message of `ctx` (or of the failed flowse_create when ctx == NULL). */
+const char* flowse_last_error(const flowse_ctx* ctx);
+
+/* Load the NCSN++ weights (EMA weights, as VFModel.eval() would select: flowmse/model.py:92-106) from a HOST blob.
+ * Replaces NCSNpp.__init__ + load_state_dict (flowmse/backbones/ncsnpp.py:45-245).  Packs the conv weights into the
+ * K-major fp16 hi/lo format of the tcgen05 kernels and uploads them; synchronous. */
+int flowse_load_weights(flowse_ctx* ctx, const float* host_blob, const flowse_tensor_desc* descs, int n);
+
+/* Bytes of device workspace the context holds for batch B, T frames (allocates the plan if needed). */
+size_t flowse_workspace_bytes(flowse_ctx* ctx, int B, int T);
+
+/* x = y + sigma * z.  Replaces FLOWMATCHING.prior_sampling (flowmse/odes.py:93-100) with z drawn by the caller
+ * (torch.randn_like on y's device keeps "same seed" semantics).  n = number of complex elements. */
+int flowse_prior_sample(flowse_ctx* ctx, const void* y, const void* z, float sigma, void* x, long long n, void* stream);
+
+/* out = NCSNpp.forward(cat([x, y], 1), t)  (flowmse/backbones/ncsnpp.py:247-404); negate != 0 gives
+ * VFModel.forward = -dnn(...) (flowmse/model.py:164-170).
+ * x, y: complex [B,1,256,T] with batch strides x_bstride / y_bstride in complex elements (so a [B,2,256,T] dnn
+ * input is passed as x = base, y = base + 256*T, strides 2*256*T).  t: fp32 [B] device.  out: complex [B,1,256,T]. */
+int flowse_ncsnpp_forward(flowse_ctx* ctx, const void* x, long long x_bstride, const void* y, long long y_bstride,
+                          const float* t, void* out, int negate, int B, int T, void* stream);
+
+/* x_out = x + v * (-stepsize).  Replaces EulerODEsolver.update_fn's arithmetic
+ * (flowmse/sampling/odesolvers.py:42-47) for a caller-supplied vector field v; n complex elements. */
+int flowse_euler_step(flowse_ctx* ctx, const void* x, const void* v, float stepsize, void* x_out, long long n,
+                      void* stream);
+
+/* The whole reverse-ODE sampler: prior sample + N solver steps with the NCSN++ vector field, entirely on device.
+ * Replaces get_white_box_solver(...)() (flowmse/sampling/__init__.py:27-62).
+ *   y, z      complex [B,1,256,T] (noisy spectrogram = conditioning, prior noise)
+ *   y_prior   mean of the prior sample x_T = y_prior + sigma z; NULL means y (evaluate.py:118 passes Y twice)
+ *   timesteps HOST fp32 [N] = torch.linspace(T_rev, t_eps, N); step sizes are their fp32 differences, last = t[N-1]
+ *   solver    FLOWSE_SOLVER_*; Heun/midpoint use an Euler step for the last interval (the reference would evaluate
+ *             the network at t = 0, i.e. log 0)
+ *   x_out     complex [B,1,256,T] */
+int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const void* z, const float* timesteps_host, int N, int solver,
+                  float sigma, void* x_out, int B, int T, void* stream);
+
+/* Options: "conv_impl" 0 = tcgen05 (default), 1 = SIMT cross-check; "graph" 0/1 = replay each NFE as a CUDA graph. */
+int flowse_set_option(flowse_ctx* ctx, const char* key, int value);
+
+/* Number of this library's kernel launches (graph kernel nodes included) since the context was created. */
+long long flowse_kernel_launches(const flowse_ctx* ctx);
+
+/* Test hook: device pointer / shape (NHWC fp32) of the output of all_modules[module_idx] from the last forward of
+ * the current (B,T) plan. */
+int flowse_debug_tap(flowse_ctx* ctx, int module_idx, const float** ptr, int* C, int* H, int* W);
+
+/* ---- op-level entry points (used by the parity tests; same kernels as the path above) ---- */
+
+/* Pack fp32 conv weights [Cout][Cin][kh*kw] (+ optional 1x1 shortcut [Cout][Cin2]) from HOST memory into a DEVICE
+ * buffer of 2*Npad*K halves (hi plane then lo plane, K = ntaps*Cin + Cin2); returns the scale exponent in *wexp. */
+int flowse_pack_conv_weights(const float* w_main_host, int Cout, int Cin, int ntaps, const float* w_sc_host, int Cin2,
+                             int Npad, void* dev_out, int* wexp);
+
+/* GroupNorm(32 groups, eps 1e-6) [+SiLU] [+FIR up/down x2] of the channel-concat of src1/src2 (NHWC fp32), written as
+ * fp16 hi/lo operands (outA: activated, outX: raw input) and/or fp32 (outF).  mode 0 plain, 1 down, 2 up. */
+int flowse_op_gn_prep(flowse_ctx* ctx, const float* src1, int C1, const float* src2, int C2, const float* gamma,
+                      const float* beta, int B, int H, int W, int mode, int silu, void* outA, void* outX, float* outF,
+                      float* outXF, void* stream);
+
+/* Implicit-GEMM conv (3x3 pad 1 when ntaps == 9, 1x1 when 1) on hi/lo operands; impl 0 = tcgen05, 1 = SIMT. */
+int flowse_op_conv_gemm(flowse_ctx* ctx, const void* A, int Cin, int ntaps, const void* X, int Cin2, const void* Wp,
+                        int Npad, int wexp, const float* bias, int bias_bstride, const float* residual, int div_sqrt2,
+                        float* out, int Cout, int ldc, int B, int H, int W, int impl, void* stream);
+
+/* Single-head spatial self-attention block (AttnBlockpp, layerspp.py:62-91) on NHWC fp32 x [B,H,W,256]. */
+int flowse_op_attention(flowse_ctx* ctx, int module_idx, const float* x, float* out, int B, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWSE_H */

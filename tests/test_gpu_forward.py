@@ -1,0 +1,123 @@
+"""Backbone / sampler parity on the GPU: CUDA path (through the C ABI) vs the CPU oracle and the committed goldens.
+Tolerance from BASELINE.json's north_star: rtol 1e-3 / atol 1e-4 fp32."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ncsnpp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-3, 1e-4
+
+
+def _c(a):
+    return torch.view_as_complex(torch.from_numpy(np.ascontiguousarray(a)))
+
+
+@pytest.fixture(scope="module")
+def ctx(synthetic_sd):
+    from flowmse_b200.lib import Context
+    c = Context(0)
+    c.load_state_dict(synthetic_sd)
+    yield c
+    c.close()
+
+
+def _close(a, b, what):
+    a, b = torch.view_as_real(a.cpu()), torch.view_as_real(b.cpu())
+    bad = (a - b).abs() > ATOL + RTOL * b.abs()
+    assert not bad.any(), f"{what}: {bad.float().mean().item():.2%} outside tolerance, max abs err {(a - b).abs().max().item():.3e}"
+
+
+def test_forward_taps_and_output_vs_golden(ctx, golden_dir, synthetic_sd):
+    g = np.load(os.path.join(golden_dir, "forward_T64.npz"))
+    x, t, v_ref = _c(g["x"]), torch.from_numpy(g["t"]), _c(g["v"])
+    ctx.set_option("graph", 0)
+    v = ctx.ncsnpp_forward(x.cuda(), t.cuda())
+    torch.cuda.synchronize()
+    report = []
+    for key in sorted((k for k in g.files if k.startswith("tap_m")), key=lambda s: int(s[5:])):
+        m = int(key[5:])
+        tap = ctx.debug_tap(m, x.shape[0]).cpu()
+        samp = tap[:, ::17, ::5, ::7].reshape(-1)[:512].numpy()
+        ref = g[key][3:]
+        err = float(np.abs(samp - ref).max())
+        report.append((m, err, float(np.abs(ref).max())))
+    worst = max(report, key=lambda r: r[1] / max(r[2], 1.0))
+    print("per-module max abs err (module, err, |ref|max):", report)
+    assert worst[1] <= 1e-3 * max(worst[2], 1.0), f"first/worst diverging module: {worst}"
+    _close(v, v_ref, "NCSNpp.forward vs reference golden")
+
+
+def test_forward_graph_replay_matches_eager(ctx, golden_dir):
+    g = np.load(os.path.join(golden_dir, "forward_T64.npz"))
+    x, t = _c(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()
+    ctx.set_option("graph", 0)
+    v0 = ctx.ncsnpp_forward(x, t)
+    ctx.set_option("graph", 1)
+    v1 = ctx.ncsnpp_forward(x, t)   # eager warm run of the plan
+    v2 = ctx.ncsnpp_forward(x, t)   # captured
+    v3 = ctx.ncsnpp_forward(x, t)   # replayed
+    assert torch.equal(torch.view_as_real(v0), torch.view_as_real(v3))
+    assert torch.equal(torch.view_as_real(v1), torch.view_as_real(v2))
+
+
+def test_forward_simt_cross_check(ctx, golden_dir):
+    """tcgen05 path vs the SIMT evaluation of the same operands: isolates tensor-core / TMA layout bugs."""
+    g = np.load(os.path.join(golden_dir, "forward_T64.npz"))
+    x, t = _c(g["x"])[:1].contiguous().cuda(), torch.from_numpy(g["t"])[:1].cuda()
+    ctx.set_option("graph", 0)
+    ctx.set_option("conv_impl", 0)
+    v_tc = ctx.ncsnpp_forward(x, t)
+    ctx.set_option("conv_impl", 1)
+    v_simt = ctx.ncsnpp_forward(x, t)
+    ctx.set_option("conv_impl", 0)
+    ctx.set_option("graph", 1)
+    _close(v_tc, v_simt, "tcgen05 vs SIMT")
+
+
+def test_vf_forward_is_negated(ctx, golden_dir):
+    g = np.load(os.path.join(golden_dir, "forward_T64.npz"))
+    xy, t = _c(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()
+    v = ctx.ncsnpp_forward(xy, t)
+    vf = ctx.vf_forward(xy[:, :1].contiguous(), t, xy[:, 1:].contiguous())
+    assert torch.equal(torch.view_as_real(vf), torch.view_as_real(-v))
+
+
+@pytest.mark.parametrize("N", [1, 5])
+def test_euler_sampler_vs_golden(ctx, golden_dir, N):
+    g = np.load(os.path.join(golden_dir, "sampler_T64.npz"))
+    Y, z = _c(g["Y"]).cuda(), _c(g["z"]).cuda()
+    ts = torch.linspace(1.0, 0.03, N)
+    x = ctx.sample(Y, z, ts, solver=0, sigma=0.487)
+    _close(x, _c(g[f"x_euler_N{N}"]), f"Euler N={N}")
+
+
+@pytest.mark.parametrize("solver,sid", [("heun", 1), ("midpoint", 2)])
+def test_heun_midpoint_vs_golden(ctx, golden_dir, solver, sid):
+    g = np.load(os.path.join(golden_dir, "sampler_T64.npz"))
+    Y, z = _c(g["Y"]).cuda(), _c(g["z"]).cuda()
+    x = ctx.sample(Y, z, torch.linspace(1.0, 0.03, 3), solver=sid, sigma=0.487)
+    _close(x, _c(g[f"x_{solver}_N3"]), f"{solver} N=3")
+
+
+def test_ragged_T128_batch2_vs_oracle(ctx, synthetic_sd):
+    """A second plan shape (T=128, B=2) against the CPU oracle computed here."""
+    g = torch.Generator().manual_seed(5)
+    Y = torch.view_as_complex(0.3 * torch.randn(2, 1, 256, 128, 2, generator=g))
+    z = torch.view_as_complex(torch.randn(2, 1, 256, 128, 2, generator=g) * np.sqrt(0.5))
+    x_ref = orc.sample(synthetic_sd, Y, z, 2)
+    x = ctx.sample(Y.cuda(), z.cuda(), torch.linspace(1.0, 0.03, 2), solver=0, sigma=0.487)
+    _close(x, x_ref, "Euler N=2, B=2, T=128")
+
+
+def test_rejects_bad_shapes(ctx):
+    from flowmse_b200.lib import FlowseError
+    Y = torch.zeros(1, 1, 256, 100, dtype=torch.complex64, device="cuda")
+    with pytest.raises(ValueError):
+        ctx.sample(Y, Y, torch.linspace(1.0, 0.03, 2))
+    Y = torch.zeros(1, 1, 256, 64, dtype=torch.complex64, device="cuda")
+    with pytest.raises(FlowseError):
+        ctx.sample(Y, Y, torch.tensor([1.0, 0.0]))
