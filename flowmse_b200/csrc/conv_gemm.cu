@@ -38,13 +38,19 @@ constexpr int BK = 64;            // fp16 elements per K block = one 128-byte sw
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int NUM_THREADS = 192;
+constexpr int kMainSlots = 3;
+constexpr int kNumSlots = kMainSlots + 1;
 
 template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN >= 128) ? 3 : 5;
-  static constexpr int TMEM_COLS = (BN < 32) ? 32 : BN;
+  // Accumulator slots in TMEM: the tensor core adds into its fp32 accumulator with round-toward-zero, one rounding
+  // per MMA, so the bias grows with the chain length.  The hi*hi products rotate over kMainSlots accumulators and
+  // the (2^-11 smaller) hi*lo + lo*hi corrections get their own; the epilogue sums the slots in IEEE fp32.
+  static constexpr int SLOT_COLS = (BN < 32) ? 32 : BN;
+  static constexpr int TMEM_COLS = kNumSlots * SLOT_COLS;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
 };
 
@@ -160,9 +166,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);   // 32 B per K step
-          ptx::mma_f16_ss(tmem_acc, dA_hi + koff, dB_hi + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          ptx::mma_f16_ss(tmem_acc, dA_hi + koff, dB_lo + koff, idesc, 1u);
-          ptx::mma_f16_ss(tmem_acc, dA_lo + koff, dB_hi + koff, idesc, 1u);
+          const int ks = kb * (BK / UMMA_K) + k;
+          const uint32_t d_main = tmem_acc + static_cast<uint32_t>((ks % kMainSlots) * C::SLOT_COLS);
+          const uint32_t d_corr = tmem_acc + static_cast<uint32_t>(kMainSlots * C::SLOT_COLS);
+          ptx::mma_f16_ss(d_main, dA_hi + koff, dB_hi + koff, idesc, ks >= kMainSlots ? 1u : 0u);
+          ptx::mma_f16_ss(d_corr, dA_hi + koff, dB_lo + koff, idesc, ks > 0 ? 1u : 0u);
+          ptx::mma_f16_ss(d_corr, dA_lo + koff, dB_hi + koff, idesc, 1u);
         }
         ptx::mma_commit(empty_bar(stage));          // frees the smem stage when these MMAs retire
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -193,6 +202,15 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(taddr, r);
       else ptx::tmem_ld_32x32b_x16(taddr, r);
       ptx::tmem_ld_wait();
+#pragma unroll
+      for (int sl = 1; sl < kNumSlots; ++sl) {
+        uint32_t r2[CH];
+        if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(sl * C::SLOT_COLS), r2);
+        else ptx::tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(sl * C::SLOT_COLS), r2);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < CH; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+      }
       if (valid) {
 #pragma unroll
         for (int j = 0; j < CH; j += 4) {

@@ -131,6 +131,7 @@ struct Plan {
   float* step_dev = nullptr;    // [1]
   float4* pyr_out = nullptr;    // final 4-plane pyramid [B,256,T,4]
   double* stats = nullptr; size_t stats_bytes = 0;
+  double* gn_partials = nullptr; unsigned* gn_counters = nullptr;
   cudaGraphExec_t graph_fwd = nullptr;      // forward, final mode 0/1 chosen at launch via separate final op
   bool graph_ready = false;
   int eager_runs = 0;   // the first evaluation of a plan runs eagerly (sets kernel attributes, surfaces errors)
@@ -157,8 +158,9 @@ struct flowse_ctx {
   int use_graph = 1;
   long long launches = 0;
   std::unique_ptr<Plan> plan;
+  cudaStream_t cap_stream = nullptr;   // capture happens here: the caller's stream may be the legacy default stream
   // scratch for op-level entry points
-  double* op_stats = nullptr;
+  double* op_stats = nullptr; double* op_partials = nullptr; unsigned* op_counters = nullptr;
   float* op_scratch = nullptr; size_t op_scratch_bytes = 0;
 };
 
@@ -357,10 +359,11 @@ struct Builder {
     Act out = new_act(r.cout, Ho, Wo);
     double* st0 = stat_slot();
     double* st1 = stat_slot();
+    double* gp = plan->gn_partials; unsigned* gc = plan->gn_counters;
     const int Bc = B;
     const float* s1 = in1.p; const int C1 = in1.C;
     const float* s2 = in2 ? in2->p : nullptr; const int C2 = in2 ? in2->C : 0;
-    push(1, [=](cudaStream_t s) { launch_gn_stats(s1, C1, s2, C2, Bc, H * W, st0, s); return 0; });
+    push(1, [=](cudaStream_t s) { launch_gn_stats(s1, C1, s2, C2, Bc, H * W, st0, gp, gc, s); return 0; });
     PrepArgs pa{};
     pa.src1 = s1; pa.C1 = C1; pa.src2 = s2; pa.C2 = C2; pa.stats = st0; pa.gamma = r.gn0_g; pa.beta = r.gn0_b;
     pa.B = B; pa.H = H; pa.W = W; pa.mode = r.down ? kPrepDown : (r.up ? kPrepUp : kPrepPlain); pa.silu = 1;
@@ -373,7 +376,7 @@ struct Builder {
     c0.B = B; c0.H = Ho; c0.W = Wo;
     { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c0, s); }); }
     float* h1 = scrH1; const int Co = r.cout;
-    push(1, [=](cudaStream_t s) { launch_gn_stats(h1, Co, nullptr, 0, Bc, Ho * Wo, st1, s); return 0; });
+    push(1, [=](cudaStream_t s) { launch_gn_stats(h1, Co, nullptr, 0, Bc, Ho * Wo, st1, gp, gc, s); return 0; });
     PrepArgs pb{};
     pb.src1 = h1; pb.C1 = Co; pb.src2 = nullptr; pb.C2 = 0; pb.stats = st1; pb.gamma = r.gn1_g; pb.beta = r.gn1_b;
     pb.B = B; pb.H = Ho; pb.W = Wo; pb.mode = kPrepPlain; pb.silu = 1; pb.outA = scrA;
@@ -393,8 +396,9 @@ struct Builder {
     const int C = a.c, H = in.H, W = in.W, L = H * W, Bc = B;
     Act out = new_act(C, H, W);
     double* st = stat_slot();
+    double* gp = plan->gn_partials; unsigned* gc = plan->gn_counters;
     const float* x = in.p;
-    push(1, [=](cudaStream_t s) { launch_gn_stats(x, C, nullptr, 0, Bc, L, st, s); return 0; });
+    push(1, [=](cudaStream_t s) { launch_gn_stats(x, C, nullptr, 0, Bc, L, st, gp, gc, s); return 0; });
     PrepArgs pa{};
     pa.src1 = x; pa.C1 = C; pa.stats = st; pa.gamma = a.gn_g; pa.beta = a.gn_b; pa.B = B; pa.H = H; pa.W = W;
     pa.mode = kPrepPlain; pa.silu = 0; pa.outF = scrF;
@@ -450,11 +454,10 @@ struct Builder {
     plan->stats_bytes = static_cast<size_t>(128) * B * kGroups * 2 * sizeof(double);
     plan->stats = ar.alloc<double>(plan->stats_bytes / sizeof(double));
 
+    plan->gn_partials = ar.alloc<double>(static_cast<size_t>(B) * gn_stats_max_blocks() * kGroups * 2);
+    plan->gn_counters = ar.alloc<unsigned>(B);      // arena is zero-initialised; the kernel restores zero
+
     // ---- the walk (ncsnpp.py:247-404) ----
-    {
-      double* st = plan->stats; const size_t nb = plan->stats_bytes;
-      push(0, [=](cudaStream_t s) { return cudaMemsetAsync(st, 0, nb, s) == cudaSuccess ? 0 : 1; });
-    }
     {
       TembWeights tw = ctx->temb; float* td = plan->t_dev; float* ta = temb_act; float* bt = bias_table; const int Bc = B;
       push(2, [=](cudaStream_t s) { launch_temb(tw, td, Bc, ta, bt, s); return 0; });
@@ -507,8 +510,9 @@ struct Builder {
       {
         const HeadW& hw = ctx->heads.at(m);
         double* st = stat_slot();
+        double* gp = plan->gn_partials; unsigned* gc = plan->gn_counters;
         const float* hp = h.p; const int C = h.C, Hh = h.H, Ww = h.W, Bc = B;
-        push(1, [=](cudaStream_t s) { launch_gn_stats(hp, C, nullptr, 0, Bc, Hh * Ww, st, s); return 0; });
+        push(1, [=](cudaStream_t s) { launch_gn_stats(hp, C, nullptr, 0, Bc, Hh * Ww, st, gp, gc, s); return 0; });
         PrepArgs pa{};
         pa.src1 = hp; pa.C1 = C; pa.stats = st; pa.gamma = hw.gn_g; pa.beta = hw.gn_b; pa.B = B; pa.H = Hh; pa.W = Ww;
         pa.mode = kPrepPlain; pa.silu = 1; pa.outA = scrA;
@@ -580,9 +584,10 @@ int run_backbone(flowse_ctx* ctx, cudaStream_t s) {
   if (ctx->use_graph && p->eager_runs >= 1) {
     if (!p->graph_ready) {
       cudaGraph_t g = nullptr;
-      CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      const int rc = run_ops(ctx, s);
-      cudaError_t e = cudaStreamEndCapture(s, &g);
+      if (!ctx->cap_stream) CK(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+      CK(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = run_ops(ctx, ctx->cap_stream);
+      cudaError_t e = cudaStreamEndCapture(ctx->cap_stream, &g);
       if (rc) { if (g) cudaGraphDestroy(g); return rc; }
       if (e != cudaSuccess) { ctx->err = std::string("graph capture: ") + cudaGetErrorString(e); return 1; }
       e = cudaGraphInstantiate(&p->graph_fwd, g, 0);
@@ -656,7 +661,10 @@ void flowse_destroy(flowse_ctx* ctx) {
     if (ctx->plan->arena) cudaFree(ctx->plan->arena);
   }
   for (void* p : ctx->dev_allocs) cudaFree(p);
+  if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
   if (ctx->op_stats) cudaFree(ctx->op_stats);
+  if (ctx->op_partials) cudaFree(ctx->op_partials);
+  if (ctx->op_counters) cudaFree(ctx->op_counters);
   if (ctx->op_scratch) cudaFree(ctx->op_scratch);
   delete ctx;
 }
@@ -810,6 +818,23 @@ int flowse_debug_tap(flowse_ctx* ctx, int module_idx, const float** ptr, int* C,
   return 0;
 }
 
+static int ensure_op_stats(flowse_ctx* ctx) {
+  if (ctx->op_stats) return 0;
+  CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_stats), 64 * kGroups * 2 * sizeof(double)));
+  CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_partials), static_cast<size_t>(64) * gn_stats_max_blocks() * kGroups * 2 * sizeof(double)));
+  CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_counters), 64 * sizeof(unsigned)));
+  CK(cudaMemset(ctx->op_counters, 0, 64 * sizeof(unsigned)));
+  return 0;
+}
+
+int flowse_debug_copy(flowse_ctx* ctx, const void* src, void* dst, size_t bytes) {
+  if (!ctx) return 2;
+  ctx->err.clear();
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+  return 0;
+}
+
 int flowse_pack_conv_weights(const float* w_main_host, int Cout, int Cin, int ntaps, const float* w_sc_host, int Cin2,
                              int Npad, void* dev_out, int* wexp) {
   const int K = ntaps * Cin + (w_sc_host ? Cin2 : 0);
@@ -828,11 +853,9 @@ int flowse_op_gn_prep(flowse_ctx* ctx, const float* src1, int C1, const float* s
   const int C = C1 + (src2 ? C2 : 0);
   if (C % 128 != 0 || C > 1024 || C1 % 4 != 0) { ctx->err = "gn_prep: channel count must be a multiple of 128 (<= 1024)"; return 2; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t sb = static_cast<size_t>(B) * kGroups * 2 * sizeof(double);
-  if (!ctx->op_stats) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_stats), 64 * kGroups * 2 * sizeof(double)));
   if (B > 64) { ctx->err = "gn_prep op: B <= 64"; return 2; }
-  CK(cudaMemsetAsync(ctx->op_stats, 0, sb, s));
-  launch_gn_stats(src1, C1, src2, C2, B, H * W, ctx->op_stats, s);
+  if (int rc = ensure_op_stats(ctx)) return rc;
+  launch_gn_stats(src1, C1, src2, C2, B, H * W, ctx->op_stats, ctx->op_partials, ctx->op_counters, s);
   PrepArgs pa{};
   pa.src1 = src1; pa.C1 = C1; pa.src2 = src2; pa.C2 = C2; pa.stats = ctx->op_stats; pa.gamma = gamma; pa.beta = beta;
   pa.B = B; pa.H = H; pa.W = W; pa.mode = mode; pa.silu = silu;
@@ -877,14 +900,13 @@ int flowse_op_attention(flowse_ctx* ctx, int module_idx, const float* x, float* 
     CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_scratch), need));
     ctx->op_scratch_bytes = need;
   }
-  if (!ctx->op_stats) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_stats), 64 * kGroups * 2 * sizeof(double)));
   if (B > 64) { ctx->err = "attention op: B <= 64"; return 2; }
+  if (int rc = ensure_op_stats(ctx)) return rc;
   float* hn = ctx->op_scratch;
   float* qkv = hn + static_cast<size_t>(B) * L * C;
   float* O = qkv + static_cast<size_t>(B) * L * 3 * C;
   float* S = O + static_cast<size_t>(B) * L * C;
-  CK(cudaMemsetAsync(ctx->op_stats, 0, static_cast<size_t>(B) * kGroups * 2 * sizeof(double), s));
-  launch_gn_stats(x, C, nullptr, 0, B, L, ctx->op_stats, s);
+  launch_gn_stats(x, C, nullptr, 0, B, L, ctx->op_stats, ctx->op_partials, ctx->op_counters, s);
   PrepArgs pa{};
   pa.src1 = x; pa.C1 = C; pa.stats = ctx->op_stats; pa.gamma = a.gn_g; pa.beta = a.gn_b; pa.B = B; pa.H = H; pa.W = W;
   pa.mode = kPrepPlain; pa.silu = 0; pa.outF = hn;

@@ -64,16 +64,18 @@ void launch_softmax_rows(float* s, int rows, int cols, cudaStream_t st);
 // ---------------------------------------------------------------------------------------------
 // GroupNorm statistics + operand preparation (kernels_gn.cu)
 // ---------------------------------------------------------------------------------------------
-// stats[b][g] = {sum, sumsq} (double) over the channel-concatenation of src1 (C1 ch) and src2 (C2 ch, may be null).
-// stats must be zeroed before the call.
+// stats[b][g] = {mean, 1/sqrt(var+eps)} (double) over the channel-concatenation of src1 (C1 ch) and src2 (C2 ch, may be
+// null).  partials: scratch of B * gn_stats_max_blocks() * 64 doubles; counters: B unsigned, zero before first use
+// (the kernel leaves them zero).  Deterministic (no floating-point atomics).
+int gn_stats_max_blocks();
 void launch_gn_stats(const float* src1, int C1, const float* src2, int C2, int B, int npix, double* stats,
-                     cudaStream_t s);
+                     double* partials, unsigned* counters, cudaStream_t s);
 
 enum PrepMode { kPrepPlain = 0, kPrepDown = 1, kPrepUp = 2 };
 struct PrepArgs {
   const float* src1; int C1;
   const float* src2; int C2;      // virtual concat [src1, src2] on the channel axis
-  const double* stats;            // [B][32][2]
+  const double* stats;            // [B][32][2] = {mean, rstd} from launch_gn_stats
   const float* gamma; const float* beta;
   int B, H, W;                    // INPUT resolution
   int mode;                       // PrepMode: output resolution is H/2 (down), 2H (up)

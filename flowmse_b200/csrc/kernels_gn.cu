@@ -28,20 +28,24 @@ __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// statistics: per (batch, group) sum and sum of squares, accumulated in double
+// statistics: per (batch, group) mean and 1/sqrt(var + eps).
+// Deterministic: block partials (fixed-order shared-memory reduce) go to a scratch array; the LAST block to finish
+// (ticket counter) sums them in block order in double and writes {mean, rstd}.  No float atomics, no memset.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ s1, int C1, const float* __restrict__ s2, int C2, int npix, int chunk,
-                double* __restrict__ stats) {
+                double* __restrict__ stats, double* __restrict__ partials, unsigned* __restrict__ counters) {
   const int C = C1 + C2;
   const int cvec = C >> 2;                 // float4 per pixel
   const int ppi = blockDim.x / cvec;       // pixels per iteration
   const int b = blockIdx.y;
-  __shared__ float gs[kGroups], gq[kGroups];
-  if (threadIdx.x < kGroups) { gs[threadIdx.x] = 0.f; gq[threadIdx.x] = 0.f; }
-  __syncthreads();
+  const int nblk = gridDim.x;
+  __shared__ float ts[256], tq[256];
+  __shared__ double fs[8][kGroups], fq[8][kGroups];
+  __shared__ bool is_last;
   const int v = threadIdx.x % cvec;
   const int pp = threadIdx.x / cvec;
+  float s = 0.f, q = 0.f;
   if (pp < ppi) {
     const int c = v << 2;
     const float* src;
@@ -49,21 +53,55 @@ gn_stats_kernel(const float* __restrict__ s1, int C1, const float* __restrict__ 
     if (c < C1) { src = s1; ld = C1; cc = c; } else { src = s2; ld = C2; cc = c - C1; }
     const int p0 = blockIdx.x * chunk;
     const int p1 = min(npix, p0 + chunk);
-    float s = 0.f, q = 0.f;
     for (int p = p0 + pp; p < p1; p += ppi) {
       const float4 x = __ldg(reinterpret_cast<const float4*>(src + (static_cast<size_t>(b) * npix + p) * ld + cc));
       s += (x.x + x.y) + (x.z + x.w);
       q += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
     }
-    const int g = c / (C / kGroups);
-    atomicAdd(&gs[g], s);
-    atomicAdd(&gq[g], q);
+  }
+  ts[threadIdx.x] = s; tq[threadIdx.x] = q;
+  __syncthreads();
+  const int vpg = cvec / kGroups;          // float4 lanes per group (1, 2, 3 or 4)
+  if (threadIdx.x < kGroups) {
+    const int g = threadIdx.x;
+    double as = 0.0, aq = 0.0;
+    for (int r = 0; r < ppi; ++r)
+      for (int j = 0; j < vpg; ++j) {
+        const int t = r * cvec + g * vpg + j;
+        as += static_cast<double>(ts[t]); aq += static_cast<double>(tq[t]);
+      }
+    double* dst = partials + ((static_cast<size_t>(b) * nblk + blockIdx.x) * kGroups + g) * 2;
+    dst[0] = as; dst[1] = aq;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(&counters[b], 1u) == static_cast<unsigned>(nblk - 1));
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  {
+    const int g = threadIdx.x & 31, part = threadIdx.x >> 5;     // 8 parts x 32 groups
+    double as = 0.0, aq = 0.0;
+    for (int k = part; k < nblk; k += 8) {
+      const double* src = partials + ((static_cast<size_t>(b) * nblk + k) * kGroups + g) * 2;
+      as += __ldcg(src); aq += __ldcg(src + 1);
+    }
+    fs[part][g] = as; fq[part][g] = aq;
   }
   __syncthreads();
   if (threadIdx.x < kGroups) {
-    atomicAdd(&stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 0], static_cast<double>(gs[threadIdx.x]));
-    atomicAdd(&stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 1], static_cast<double>(gq[threadIdx.x]));
+    const int g = threadIdx.x;
+    double as = 0.0, aq = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { as += fs[k][g]; aq += fq[k][g]; }
+    const double n = static_cast<double>(npix) * (C / kGroups);
+    const double mean = as / n;
+    double var = aq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[(static_cast<size_t>(b) * kGroups + g) * 2 + 0] = mean;
+    stats[(static_cast<size_t>(b) * kGroups + g) * 2 + 1] = 1.0 / sqrt(var + static_cast<double>(kGnEps));
   }
+  if (threadIdx.x == 0) counters[b] = 0u;    // ready for the next GroupNorm on this stream
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -104,14 +142,8 @@ gn_prep_kernel(const PrepK k) {
   const int b = blockIdx.y;
   __shared__ float s_mean[kGroups], s_rstd[kGroups];
   if (threadIdx.x < kGroups) {
-    const double n = static_cast<double>(k.H) * k.W * (C / kGroups);
-    const double su = k.stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 0];
-    const double sq = k.stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 1];
-    const double mean = su / n;
-    double var = sq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = static_cast<float>(mean);
-    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
+    s_mean[threadIdx.x] = static_cast<float>(k.stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 0]);
+    s_rstd[threadIdx.x] = static_cast<float>(k.stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 1]);
   }
   __syncthreads();
   const size_t total = static_cast<size_t>(k.Ho) * k.Wo * cvec;
@@ -198,17 +230,19 @@ gn_prep_kernel(const PrepK k) {
 
 }  // namespace
 
+int gn_stats_max_blocks() { return 296; }
+
 void launch_gn_stats(const float* src1, int C1, const float* src2, int C2, int B, int npix, double* stats,
-                     cudaStream_t s) {
+                     double* partials, unsigned* counters, cudaStream_t s) {
   const int C = C1 + (src2 ? C2 : 0);
   const int cvec = C / 4;
   const int ppi = 256 / cvec;
-  int target_blocks = std::max(1, 592 / B);
+  int target_blocks = std::max(1, std::min(gn_stats_max_blocks(), 592 / B));
   int chunk = (npix + target_blocks - 1) / target_blocks;
   chunk = ((chunk + ppi - 1) / ppi) * ppi;
   if (chunk < ppi * 4) chunk = ppi * 4;
   dim3 grid((npix + chunk - 1) / chunk, B);
-  gn_stats_kernel<<<grid, 256, 0, s>>>(src1, C1, src2, src2 ? C2 : 0, npix, chunk, stats);
+  gn_stats_kernel<<<grid, 256, 0, s>>>(src1, C1, src2, src2 ? C2 : 0, npix, chunk, stats, partials, counters);
 }
 
 void launch_gn_prep(const PrepArgs& a, cudaStream_t s) {

@@ -48,6 +48,7 @@ def load_library():
     lib.flowse_kernel_launches.argtypes = [vp]; lib.flowse_kernel_launches.restype = ll
     lib.flowse_debug_tap.argtypes = [vp, i, C.POINTER(vp), C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     lib.flowse_debug_tap.restype = i
+    lib.flowse_debug_copy.argtypes = [vp, vp, vp, C.c_size_t]; lib.flowse_debug_copy.restype = i
     lib.flowse_pack_conv_weights.argtypes = [vp, i, i, i, vp, i, i, vp, C.POINTER(i)]
     lib.flowse_pack_conv_weights.restype = i
     lib.flowse_op_gn_prep.argtypes = [vp, vp, i, vp, i, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp]
@@ -62,7 +63,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "flowse_create", "flowse_destroy", "flowse_last_error", "flowse_load_weights", "flowse_workspace_bytes",
     "flowse_prior_sample", "flowse_ncsnpp_forward", "flowse_euler_step", "flowse_sample", "flowse_set_option",
-    "flowse_kernel_launches", "flowse_debug_tap", "flowse_pack_conv_weights", "flowse_op_gn_prep",
+    "flowse_kernel_launches", "flowse_debug_tap", "flowse_debug_copy", "flowse_pack_conv_weights", "flowse_op_gn_prep",
     "flowse_op_conv_gemm", "flowse_op_attention",
 ]
 
@@ -205,9 +206,7 @@ class Context:
         self._check(self._lib.flowse_debug_tap(self._h, module_idx, C.byref(p), C.byref(c), C.byref(h), C.byref(w)))
         n = B * h.value * w.value * c.value
         out = torch.empty(n, dtype=torch.float32, device=f"cuda:{self.device}")
-        torch.cuda.synchronize()
-        rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), p.value, n * 4, 3)
-        assert int(rc) == 0
+        self._check(self._lib.flowse_debug_copy(self._h, p.value, out.data_ptr(), n * 4))
         return out.view(B, h.value, w.value, c.value).permute(0, 3, 1, 2).contiguous()
 
     def pack_conv_weights(self, w_main: torch.Tensor, w_sc: Optional[torch.Tensor], npad: int):

@@ -85,6 +85,9 @@ long long flowse_kernel_launches(const flowse_ctx* ctx);
  * the current (B,T) plan. */
 int flowse_debug_tap(flowse_ctx* ctx, int module_idx, const float** ptr, int* C, int* H, int* W);
 
+/* Test hook: synchronous device-to-device copy (pairs with flowse_debug_tap). */
+int flowse_debug_copy(flowse_ctx* ctx, const void* src, void* dst, size_t bytes);
+
 /* ---- op-level entry points (used by the parity tests; same kernels as the path above) ---- */
 
 /* Pack fp32 conv weights [Cout][Cin][kh*kw] (+ optional 1x1 shortcut [Cout][Cin2]) from HOST memory into a DEVICE
