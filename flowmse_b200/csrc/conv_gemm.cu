@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 
 namespace flowse {
@@ -37,7 +38,8 @@ constexpr int BM = 128;
 constexpr int BK = 64;            // fp16 elements per K block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quadrant)
+constexpr int kEpiWarps = 8;
 constexpr int kMainSlots = 3;
 constexpr int kNumSlots = kMainSlots + 1;
 
@@ -51,7 +53,12 @@ struct Cfg {
   // the (2^-11 smaller) hi*lo + lo*hi corrections get their own; the epilogue sums the slots in IEEE fp32.
   static constexpr int SLOT_COLS = (BN < 32) ? 32 : BN;
   static constexpr int TMEM_COLS = kNumSlots * SLOT_COLS;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  // epilogue staging: 8 warps x 32 rows x (CH + 4) floats, so that global loads/stores are row-contiguous
+  static constexpr int CH = 16;                             // accumulator columns handled per epilogue pass
+  static constexpr int STG_STRIDE = CH + 4;                 // floats; +4 keeps both access phases conflict-free
+  static constexpr int STG_BYTES = kEpiWarps * 32 * STG_STRIDE * 4;
+  static constexpr int COLS_PER_WARP = (BN >= 32) ? BN / 2 : BN;   // each quadrant's columns are split over 2 warps
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024;
 };
 
 struct GemmParams {
@@ -64,6 +71,7 @@ struct GemmParams {
   const float* residual;
   float* out;
   int div_sqrt2;
+  long long* dbg;   // optional per-CTA phase timestamps (FLOWSE_CONV_DBG=1), else null
 };
 
 template <int BN>
@@ -84,6 +92,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+  auto stamp = [&](int slot) { if (p.dbg) p.dbg[static_cast<size_t>(cta_lin) * 8 + slot] = static_cast<long long>(ptx::globaltimer_ns()); };
+  if (threadIdx.x == 0) stamp(0);
 
   // tile coordinates
   int m_tile = blockIdx.x;
@@ -116,6 +127,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot_ptr;
+  if (threadIdx.x == 0) stamp(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -155,6 +167,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int kb = 0; kb < nkb; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
+        if (kb == 0) stamp(2);
         const uint32_t sA_hi = smem_base + stage * C::STAGE_BYTES;
         const uint32_t sA_lo = sA_hi + A_BYTES;
         const uint32_t sB_hi = sA_lo + A_BYTES;
@@ -179,70 +192,112 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       ptx::mma_commit(tmem_full_bar);               // accumulator complete
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quadrant, each owning half of the tile's columns, CH columns per pass.
+    // Phase A: TMEM -> registers (lane = tile row), the accumulator slots summed in fp32, written to a padded smem
+    //          staging tile.  Phase B: the warp re-reads the tile row-wise so that every global access (residual,
+    //          output) is a contiguous 64-byte run per row: LPR lanes cover one row's CH columns, RPI rows per pass.
+    // Everything that does not depend on the accumulator (pixel offsets, bias, first residual block) is done
+    // before waiting for the MMAs, i.e. overlapped with the main loop.
+    const int e = warp - 2;
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;
-    const int th = row / p.TW;
-    const int tw = row - th * p.TW;
-    const int h = h0 + th, w = w0 + tw;
-    const bool valid = (h < p.H) && (w < p.W);
-    const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
-    float* orow = p.out + pix * p.ldc;
-    const float* rrow = p.residual ? p.residual + pix * p.ldc : nullptr;
+    const int half = e >> 2;
+    constexpr int CH = C::CH;
+    constexpr int LPR = CH / 4;                      // lanes per row (float4 each)
+    constexpr int RPI = 32 / LPR;                    // rows per pass
+    constexpr int NIT = 32 / RPI;                    // passes over the 32 rows
+    constexpr int NCHUNK = C::COLS_PER_WARP / CH;
+    const bool active = (BN >= 32) || (half == 0);
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - ptx::smem_u32(smem_raw)) +
+                                          C::STAGES * C::STAGE_BYTES) + e * 32 * C::STG_STRIDE;
     const float* brow = p.bias + static_cast<size_t>(b) * p.bias_bstride;
+    const int sub_row = lane / LPR;
+    const int cj = (lane % LPR) * 4;
+    const int col_base = half * C::COLS_PER_WARP;
+    long long off[NIT];                              // element offset of (pixel, n0 + col_base + cj), -1 if outside
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int row = q * 32 + it * RPI + sub_row;
+      const int th = row / p.TW;
+      const int tw = row - th * p.TW;
+      const int h = h0 + th, w = w0 + tw;
+      off[it] = (h < p.H && w < p.W)
+                    ? static_cast<long long>((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.ldc + n0 + col_base + cj
+                    : -1;
+    }
+    float4 res[NIT];
+    auto load_res = [&](int c0) {
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.residual && off[it] >= 0 && n0 + col_base + c0 + cj < p.Cout)
+          res[it] = __ldg(reinterpret_cast<const float4*>(p.residual + off[it] + c0));
+      }
+    };
+    if (active) load_res(0);
+    const float post = p.div_sqrt2 ? 0.70710678118654752440f : 1.0f;
 
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after();
+    if (threadIdx.x == 64) stamp(3);
 
-    constexpr int CH = (BN >= 32) ? 32 : 16;
+    if (active) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += CH) {
-      uint32_t r[CH];
-      const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
-      if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(taddr, r);
-      else ptx::tmem_ld_32x32b_x16(taddr, r);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int sl = 1; sl < kNumSlots; ++sl) {
-        uint32_t r2[CH];
-        if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(sl * C::SLOT_COLS), r2);
-        else ptx::tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(sl * C::SLOT_COLS), r2);
+      for (int ci = 0; ci < NCHUNK; ++ci) {
+        const int c0 = ci * CH;
+        uint32_t r[CH], r2[CH];
+        const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(col_base + c0);
+        ptx::tmem_ld_32x32b_x16(taddr, r);
+        ptx::tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(C::SLOT_COLS), r2);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < CH; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
-      }
-      if (valid) {
+        uint32_t r3[CH];
+        ptx::tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(2 * C::SLOT_COLS), r2);
+        ptx::tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(3 * C::SLOT_COLS), r3);
+        ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < CH; j += 4) {
-          const int n = n0 + c0 + j;
-          if (n < p.Cout) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(brow + n));
-            float4 v;
-            v.x = __uint_as_float(r[j + 0]) * p.wscale_inv + bv.x;
-            v.y = __uint_as_float(r[j + 1]) * p.wscale_inv + bv.y;
-            v.z = __uint_as_float(r[j + 2]) * p.wscale_inv + bv.z;
-            v.w = __uint_as_float(r[j + 3]) * p.wscale_inv + bv.w;
-            if (rrow) {
-              const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + n));
-              v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+        for (int j = 0; j < CH; ++j)
+          r[j] = __float_as_uint((__uint_as_float(r[j]) + __uint_as_float(r2[j])) + __uint_as_float(r3[j]));
+        __syncwarp();                                // previous pass has finished reading the staging tile
+#pragma unroll
+        for (int j = 0; j < CH; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * C::STG_STRIDE + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                          __uint_as_float(r[j + 3]));
+        __syncwarp();
+        const int n = n0 + col_base + c0 + cj;
+        float4 cur[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) cur[it] = res[it];
+        if (ci + 1 < NCHUNK) load_res(c0 + CH);        // next pass's residual block in flight during this one
+        if (n < p.Cout) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(brow + n));
+#pragma unroll
+          for (int it = 0; it < NIT; ++it) {
+            if (off[it] >= 0) {
+              const float4 a = *reinterpret_cast<const float4*>(stg + (it * RPI + sub_row) * C::STG_STRIDE + cj);
+              float4 v;
+              v.x = (a.x * p.wscale_inv + bv.x + cur[it].x) * post;
+              v.y = (a.y * p.wscale_inv + bv.y + cur[it].y) * post;
+              v.z = (a.z * p.wscale_inv + bv.z + cur[it].z) * post;
+              v.w = (a.w * p.wscale_inv + bv.w + cur[it].w) * post;
+              *reinterpret_cast<float4*>(p.out + off[it] + c0) = v;
             }
-            if (p.div_sqrt2) {
-              v.x = __fdiv_rn(v.x, kSqrt2); v.y = __fdiv_rn(v.y, kSqrt2);
-              v.z = __fdiv_rn(v.z, kSqrt2); v.w = __fdiv_rn(v.w, kSqrt2);
-            }
-            *reinterpret_cast<float4*>(orow + n) = v;
           }
         }
       }
     }
   }
 
+  if (threadIdx.x == 64) stamp(4);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_acc, C::TMEM_COLS);
   }
+  if (threadIdx.x == 32) stamp(5);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -383,6 +438,7 @@ GemmParams make_params(const ConvGemmArgs& a) {
   p.residual = a.residual;
   p.out = a.out;
   p.div_sqrt2 = a.div_sqrt2;
+  p.dbg = nullptr;
   return p;
 }
 
@@ -416,7 +472,26 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   else tmX = tmA;
   if (!make_w_map(&tmW, a.Wp, a.Npad, K, BN, err)) return 1;
   dim3 grid(a.B * p.tiles_w * p.tiles_h, (a.Cout + BN - 1) / BN);
+  static const bool dbg = getenv("FLOWSE_CONV_DBG") != nullptr;
+  long long* dbuf = nullptr;
+  const size_t ncta = static_cast<size_t>(grid.x) * grid.y;
+  if (dbg) { cudaMalloc(&dbuf, ncta * 8 * sizeof(long long)); cudaMemset(dbuf, 0, ncta * 8 * sizeof(long long)); p.dbg = dbuf; }
   conv_gemm_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(tmA, tmX, tmW, p);
+  if (dbg) {
+    cudaStreamSynchronize(s);
+    std::vector<long long> h(ncta * 8);
+    cudaMemcpy(h.data(), dbuf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dbuf);
+    double ph[5] = {0, 0, 0, 0, 0};
+    long long tmin = h[0], tmax = 0;
+    for (size_t c = 0; c < ncta; ++c) {
+      for (int k = 0; k < 5; ++k) ph[k] += static_cast<double>(h[c * 8 + k + 1] - h[c * 8 + k]);
+      tmin = std::min(tmin, h[c * 8]); tmax = std::max(tmax, h[c * 8 + 5]);
+    }
+    fprintf(stderr, "[conv dbg] ctas=%zu kb=%d  setup %.2f us | first-data %.2f | mainloop %.2f | epilogue %.2f | teardown %.2f | kernel span %.2f us\n",
+            ncta, p.ntaps * p.nchunk_main + p.nchunk_sc, ph[0] / ncta / 1e3, ph[1] / ncta / 1e3, ph[2] / ncta / 1e3,
+            ph[3] / ncta / 1e3, ph[4] / ncta / 1e3, (tmax - tmin) / 1e3);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv_gemm launch: ") + cudaGetErrorString(e); return 1; }
   return 0;

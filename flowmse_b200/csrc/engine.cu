@@ -116,7 +116,8 @@ struct HeadW { int c = 0; float *gn_g = nullptr, *gn_b = nullptr, *bias = nullpt
 
 struct Act { float* p = nullptr; int C = 0, H = 0, W = 0; };
 
-struct Op { std::function<int(cudaStream_t)> fn; int nk; };
+// kind: 0 misc, 1 gn_stats, 2 gn_prep, 3 conv_gemm, 4 attention, 5 small 4-channel / input kernels, 6 time embedding
+struct Op { std::function<int(cudaStream_t)> fn; int nk; int kind; double flops; int info[4]; };
 
 struct Plan {
   int B = 0, T = 0;
@@ -336,8 +337,13 @@ struct Builder {
   float *scrH1 = nullptr, *scrF = nullptr, *scrQKV = nullptr, *scrS = nullptr, *scrO = nullptr, *scrHead = nullptr;
   float *temb_act = nullptr, *bias_table = nullptr;
 
-  void push(int nk, std::function<int(cudaStream_t)> fn) {
-    if (!dry) plan->ops.push_back(Op{std::move(fn), nk});
+  void push(int nk, std::function<int(cudaStream_t)> fn, int kind = 0, double flops = 0.0, int i0 = 0, int i1 = 0,
+            int i2 = 0, int i3 = 0) {
+    if (!dry) plan->ops.push_back(Op{std::move(fn), nk, kind, flops, {i0, i1, i2, i3}});
+  }
+  static double conv_flops(const ConvGemmArgs& a) {
+    const double K = static_cast<double>(a.ntaps) * a.Cin + (a.X ? a.Cin2 : 0);
+    return 2.0 * a.B * a.H * a.W * a.Cout * K;
   }
   double* stat_slot() {
     double* p = plan->stats ? plan->stats + static_cast<size_t>(stat_slots) * B * kGroups * 2 : nullptr;
@@ -363,30 +369,30 @@ struct Builder {
     const int Bc = B;
     const float* s1 = in1.p; const int C1 = in1.C;
     const float* s2 = in2 ? in2->p : nullptr; const int C2 = in2 ? in2->C : 0;
-    push(1, [=](cudaStream_t s) { launch_gn_stats(s1, C1, s2, C2, Bc, H * W, st0, gp, gc, s); return 0; });
+    push(1, [=](cudaStream_t s) { launch_gn_stats(s1, C1, s2, C2, Bc, H * W, st0, gp, gc, s); return 0; }, 1);
     PrepArgs pa{};
     pa.src1 = s1; pa.C1 = C1; pa.src2 = s2; pa.C2 = C2; pa.stats = st0; pa.gamma = r.gn0_g; pa.beta = r.gn0_b;
     pa.B = B; pa.H = H; pa.W = W; pa.mode = r.down ? kPrepDown : (r.up ? kPrepUp : kPrepPlain); pa.silu = 1;
     pa.outA = scrA; pa.outX = r.has_sc ? scrX : nullptr;
-    push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; });
+    push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; }, 2);
     ConvGemmArgs c0{};
     c0.A = scrA; c0.Cin = Cin; c0.ntaps = 9; c0.X = nullptr; c0.Cin2 = 0; c0.Wp = r.conv0.wp; c0.Npad = r.conv0.Npad;
     c0.wscale_inv = r.conv0.wscale_inv; c0.bias = bias_table + r.dense_off; c0.bias_bstride = ctx->dense_rows;
     c0.residual = nullptr; c0.div_sqrt2 = 0; c0.out = scrH1; c0.Cout = r.cout; c0.ldc = r.cout;
     c0.B = B; c0.H = Ho; c0.W = Wo;
-    { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c0, s); }); }
+    { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c0, s); }, 3, conv_flops(c0), c0.H, c0.W, c0.ntaps * c0.Cin + (c0.X ? c0.Cin2 : 0), c0.Cout); }
     float* h1 = scrH1; const int Co = r.cout;
-    push(1, [=](cudaStream_t s) { launch_gn_stats(h1, Co, nullptr, 0, Bc, Ho * Wo, st1, gp, gc, s); return 0; });
+    push(1, [=](cudaStream_t s) { launch_gn_stats(h1, Co, nullptr, 0, Bc, Ho * Wo, st1, gp, gc, s); return 0; }, 1);
     PrepArgs pb{};
     pb.src1 = h1; pb.C1 = Co; pb.src2 = nullptr; pb.C2 = 0; pb.stats = st1; pb.gamma = r.gn1_g; pb.beta = r.gn1_b;
     pb.B = B; pb.H = Ho; pb.W = Wo; pb.mode = kPrepPlain; pb.silu = 1; pb.outA = scrA;
-    push(1, [=](cudaStream_t s) { launch_gn_prep(pb, s); return 0; });
+    push(1, [=](cudaStream_t s) { launch_gn_prep(pb, s); return 0; }, 2);
     ConvGemmArgs c1{};
     c1.A = scrA; c1.Cin = Co; c1.ntaps = 9; c1.X = r.has_sc ? scrX : nullptr; c1.Cin2 = r.has_sc ? Cin : 0;
     c1.Wp = r.conv1.wp; c1.Npad = r.conv1.Npad; c1.wscale_inv = r.conv1.wscale_inv; c1.bias = r.bias1;
     c1.bias_bstride = 0; c1.residual = r.has_sc ? nullptr : s1; c1.div_sqrt2 = 1; c1.out = out.p; c1.Cout = Co;
     c1.ldc = Co; c1.B = B; c1.H = Ho; c1.W = Wo;
-    { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c1, s); }); }
+    { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c1, s); }, 3, conv_flops(c1), c1.H, c1.W, c1.ntaps * c1.Cin + (c1.X ? c1.Cin2 : 0), c1.Cout); }
     plan->taps[mi] = out;
     return out;
   }
@@ -398,34 +404,34 @@ struct Builder {
     double* st = stat_slot();
     double* gp = plan->gn_partials; unsigned* gc = plan->gn_counters;
     const float* x = in.p;
-    push(1, [=](cudaStream_t s) { launch_gn_stats(x, C, nullptr, 0, Bc, L, st, gp, gc, s); return 0; });
+    push(1, [=](cudaStream_t s) { launch_gn_stats(x, C, nullptr, 0, Bc, L, st, gp, gc, s); return 0; }, 1);
     PrepArgs pa{};
     pa.src1 = x; pa.C1 = C; pa.stats = st; pa.gamma = a.gn_g; pa.beta = a.gn_b; pa.B = B; pa.H = H; pa.W = W;
     pa.mode = kPrepPlain; pa.silu = 0; pa.outF = scrF;
-    push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; });
+    push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; }, 2);
     float *hn = scrF, *qkv = scrQKV, *S = scrS, *O = scrO, *o = out.p;
     push(1, [=](cudaStream_t s) {   // q,k,v = NIN_0..2(h)
       SgemmArgs g{}; g.A = hn; g.lda = C; g.Bm = a.wqkv; g.ldb = 3 * C; g.transB = 0; g.C = qkv; g.ldc = 3 * C;
       g.M = Bc * L; g.N = 3 * C; g.K = C; g.batch = 1; g.alpha = 1.f; g.bias = a.bqkv;
-      launch_sgemm(g, s); return 0; });
+      launch_sgemm(g, s); return 0; }, 4);
     push(1, [=](cudaStream_t s) {   // w = q.k^T * C^-0.5
       SgemmArgs g{}; g.A = qkv; g.lda = 3 * C; g.strideA = static_cast<long long>(L) * 3 * C;
       g.Bm = qkv + C; g.ldb = 3 * C; g.strideB = g.strideA; g.transB = 1;
       g.C = S; g.ldc = L; g.strideC = static_cast<long long>(L) * L; g.M = L; g.N = L; g.K = C; g.batch = Bc;
       g.alpha = 1.0f / sqrtf(static_cast<float>(C));
-      launch_sgemm(g, s); return 0; });
-    push(1, [=](cudaStream_t s) { launch_softmax_rows(S, Bc * L, L, s); return 0; });
+      launch_sgemm(g, s); return 0; }, 4);
+    push(1, [=](cudaStream_t s) { launch_softmax_rows(S, Bc * L, L, s); return 0; }, 4);
     push(1, [=](cudaStream_t s) {   // h = w.v
       SgemmArgs g{}; g.A = S; g.lda = L; g.strideA = static_cast<long long>(L) * L;
       g.Bm = qkv + 2 * C; g.ldb = 3 * C; g.strideB = static_cast<long long>(L) * 3 * C; g.transB = 0;
       g.C = O; g.ldc = C; g.strideC = static_cast<long long>(L) * C; g.M = L; g.N = C; g.K = L; g.batch = Bc;
       g.alpha = 1.f;
-      launch_sgemm(g, s); return 0; });
+      launch_sgemm(g, s); return 0; }, 4);
     push(1, [=](cudaStream_t s) {   // (x + NIN_3(h)) / sqrt(2)
       SgemmArgs g{}; g.A = O; g.lda = C; g.Bm = a.w3; g.ldb = C; g.transB = 0; g.C = o; g.ldc = C;
       g.M = Bc * L; g.N = C; g.K = C; g.batch = 1; g.alpha = 1.f; g.bias = a.b3; g.residual = x; g.ldr = C;
       g.div_sqrt2 = 1;
-      launch_sgemm(g, s); return 0; });
+      launch_sgemm(g, s); return 0; }, 4);
     plan->taps[mi] = out;
     return out;
   }
@@ -460,7 +466,7 @@ struct Builder {
     // ---- the walk (ncsnpp.py:247-404) ----
     {
       TembWeights tw = ctx->temb; float* td = plan->t_dev; float* ta = temb_act; float* bt = bias_table; const int Bc = B;
-      push(2, [=](cudaStream_t s) { launch_temb(tw, td, Bc, ta, bt, s); return 0; });
+      push(2, [=](cudaStream_t s) { launch_temb(tw, td, Bc, ta, bt, s); return 0; }, 6);
     }
     std::vector<float4*> pin(kNumLevels);
     for (int l = 0; l < kNumLevels; ++l) pin[l] = ar.alloc<float4>(static_cast<size_t>(B) * (H0 >> l) * (W0 >> l));
@@ -469,7 +475,7 @@ struct Builder {
     {
       const float2 *px = plan->x, *py = plan->y; const float *w = ctx->conv_in_w, *bb = ctx->conv_in_b;
       float* o = h0.p; float4* p0 = pin[0]; const int Bc = B;
-      push(1, [=](cudaStream_t s) { launch_conv_in(px, py, w, bb, o, p0, Bc, H0, W0, s); return 0; });
+      push(1, [=](cudaStream_t s) { launch_conv_in(px, py, w, bb, o, p0, Bc, H0, W0, s); return 0; }, 5);
     }
     plan->taps[3] = h0;
     ++m;
@@ -488,8 +494,8 @@ struct Builder {
         {
           const float4* src = pin[l]; float4* dst = pin[l + 1]; const int Bc = B, Hh = h.H, Ww = h.W, C = cw.c;
           const float* hp = h.p; float* op = o.p; const float *w = cw.w, *bb = cw.b;
-          push(1, [=](cudaStream_t s) { launch_fir_down4(src, dst, Bc, Hh, Ww, s); return 0; });
-          push(1, [=](cudaStream_t s) { launch_combine(hp, dst, w, bb, op, Bc, Hh, Ww, C, s); return 0; });
+          push(1, [=](cudaStream_t s) { launch_fir_down4(src, dst, Bc, Hh, Ww, s); return 0; }, 5);
+          push(1, [=](cudaStream_t s) { launch_combine(hp, dst, w, bb, op, Bc, Hh, Ww, C, s); return 0; }, 5);
         }
         plan->taps[m] = o;
         h = o; ++m;
@@ -512,18 +518,18 @@ struct Builder {
         double* st = stat_slot();
         double* gp = plan->gn_partials; unsigned* gc = plan->gn_counters;
         const float* hp = h.p; const int C = h.C, Hh = h.H, Ww = h.W, Bc = B;
-        push(1, [=](cudaStream_t s) { launch_gn_stats(hp, C, nullptr, 0, Bc, Hh * Ww, st, gp, gc, s); return 0; });
+        push(1, [=](cudaStream_t s) { launch_gn_stats(hp, C, nullptr, 0, Bc, Hh * Ww, st, gp, gc, s); return 0; }, 1);
         PrepArgs pa{};
         pa.src1 = hp; pa.C1 = C; pa.stats = st; pa.gamma = hw.gn_g; pa.beta = hw.gn_b; pa.B = B; pa.H = Hh; pa.W = Ww;
         pa.mode = kPrepPlain; pa.silu = 1; pa.outA = scrA;
-        push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; });
+        push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; }, 2);
         ConvGemmArgs c{};
         c.A = scrA; c.Cin = C; c.ntaps = 9; c.Wp = hw.conv.wp; c.Npad = hw.conv.Npad; c.wscale_inv = hw.conv.wscale_inv;
         c.bias = hw.bias; c.bias_bstride = 0; c.out = scrHead; c.Cout = 4; c.ldc = 4; c.B = B; c.H = Hh; c.W = Ww;
-        { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c, s); }); }
+        { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c, s); }, 3, conv_flops(c), c.H, c.W, c.ntaps * c.Cin + (c.X ? c.Cin2 : 0), c.Cout); }
         float4* pyr = ar.alloc<float4>(static_cast<size_t>(B) * Hh * Ww);
         const float4* prev = pyr_prev; const float4* head = reinterpret_cast<const float4*>(scrHead);
-        push(1, [=](cudaStream_t s) { launch_pyr_accum(prev, head, pyr, Bc, Hh, Ww, s); return 0; });
+        push(1, [=](cudaStream_t s) { launch_pyr_accum(prev, head, pyr, Bc, Hh, Ww, s); return 0; }, 5);
         Act tp; tp.p = reinterpret_cast<float*>(pyr); tp.C = 4; tp.H = Hh; tp.W = Ww;
         plan->taps[m + 1] = tp;
         pyr_prev = pyr;
@@ -787,6 +793,37 @@ int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const voi
   }
   CK(cudaMemcpyAsync(x_out, p->x, n * sizeof(float2), cudaMemcpyDeviceToDevice, s));
   CK(cudaGetLastError());
+  return 0;
+}
+
+int flowse_profile_forward(flowse_ctx* ctx, int max_ops, int* kinds, float* ms, double* flops, int* info, int* n_ops) {
+  if (!ctx) return 2;
+  ctx->err.clear();
+  if (!ctx->plan) { ctx->err = "no plan yet: run a forward or a sampler first"; return 2; }
+  Plan* p = ctx->plan.get();
+  const int n = static_cast<int>(p->ops.size());
+  if (n > max_ops) { ctx->err = "profile_forward: buffer too small"; return 2; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = nullptr;
+  CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(ev[0], s));
+  for (int i = 0; i < n; ++i) {
+    if (int rc = p->ops[i].fn(s)) return rc;
+    CK(cudaEventRecord(ev[i + 1], s));
+  }
+  CK(cudaStreamSynchronize(s));
+  for (int i = 0; i < n; ++i) {
+    CK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    kinds[i] = p->ops[i].kind; flops[i] = p->ops[i].flops;
+    for (int k = 0; k < 4; ++k) info[4 * i + k] = p->ops[i].info[k];
+  }
+  *n_ops = n;
+  for (auto& e : ev) cudaEventDestroy(e);
+  cudaStreamDestroy(s);
+  ctx->launches += p->kernels_per_forward;
   return 0;
 }
 

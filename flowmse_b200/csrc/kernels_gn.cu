@@ -53,11 +53,26 @@ gn_stats_kernel(const float* __restrict__ s1, int C1, const float* __restrict__ 
     if (c < C1) { src = s1; ld = C1; cc = c; } else { src = s2; ld = C2; cc = c - C1; }
     const int p0 = blockIdx.x * chunk;
     const int p1 = min(npix, p0 + chunk);
-    for (int p = p0 + pp; p < p1; p += ppi) {
-      const float4 x = __ldg(reinterpret_cast<const float4*>(src + (static_cast<size_t>(b) * npix + p) * ld + cc));
+    const float* base = src + static_cast<size_t>(b) * npix * ld + cc;
+    int p = p0 + pp;
+    float s1a = 0.f, q1a = 0.f, s2a = 0.f, q2a = 0.f, s3a = 0.f, q3a = 0.f;
+    for (; p + 3 * ppi < p1; p += 4 * ppi) {        // 4 independent 16-byte loads in flight per thread
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * ld));
+      const float4 x1 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + ppi) * ld));
+      const float4 x2 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + 2 * ppi) * ld));
+      const float4 x3 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + 3 * ppi) * ld));
+      s += (x0.x + x0.y) + (x0.z + x0.w);   q += (x0.x * x0.x + x0.y * x0.y) + (x0.z * x0.z + x0.w * x0.w);
+      s1a += (x1.x + x1.y) + (x1.z + x1.w); q1a += (x1.x * x1.x + x1.y * x1.y) + (x1.z * x1.z + x1.w * x1.w);
+      s2a += (x2.x + x2.y) + (x2.z + x2.w); q2a += (x2.x * x2.x + x2.y * x2.y) + (x2.z * x2.z + x2.w * x2.w);
+      s3a += (x3.x + x3.y) + (x3.z + x3.w); q3a += (x3.x * x3.x + x3.y * x3.y) + (x3.z * x3.z + x3.w * x3.w);
+    }
+    for (; p < p1; p += ppi) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * ld));
       s += (x.x + x.y) + (x.z + x.w);
       q += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
     }
+    s = (s + s1a) + (s2a + s3a);
+    q = (q + q1a) + (q2a + q3a);
   }
   ts[threadIdx.x] = s; tq[threadIdx.x] = q;
   __syncthreads();
@@ -228,6 +243,63 @@ gn_prep_kernel(const PrepK k) {
   }
 }
 
+// Plain (no resampling) variant: 8 channels per thread -> two 16-byte loads in flight and 16-byte fp16 stores.
+__device__ __forceinline__ uint4 pack8(const uint2 a, const uint2 b) { return make_uint4(a.x, a.y, b.x, b.y); }
+
+__global__ void __launch_bounds__(256)
+gn_prep_plain8_kernel(const PrepK k) {
+  const int C = k.C1 + k.C2;
+  const int c8 = C >> 3;
+  const int cpg = C / kGroups;
+  const int b = blockIdx.y;
+  __shared__ float s_mean[kGroups], s_rstd[kGroups];
+  if (threadIdx.x < kGroups) {
+    s_mean[threadIdx.x] = static_cast<float>(k.stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 0]);
+    s_rstd[threadIdx.x] = static_cast<float>(k.stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 1]);
+  }
+  __syncthreads();
+  const size_t npix = static_cast<size_t>(k.H) * k.W;
+  const size_t total = npix * c8;
+  const size_t plane = static_cast<size_t>(k.B) * npix * C;
+  for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = idx % c8;
+    const size_t pix = static_cast<size_t>(b) * npix + idx / c8;
+    const int c = v << 3;
+    const float* src = (c < k.C1) ? k.s1 + pix * k.C1 + c : k.s2 + pix * k.C2 + (c - k.C1);
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 x1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+    const float4 ga0 = __ldg(reinterpret_cast<const float4*>(k.gamma + c));
+    const float4 ga1 = __ldg(reinterpret_cast<const float4*>(k.gamma + c + 4));
+    const float4 be0 = __ldg(reinterpret_cast<const float4*>(k.beta + c));
+    const float4 be1 = __ldg(reinterpret_cast<const float4*>(k.beta + c + 4));
+    const int g0 = c / cpg, g1 = (c + 4) / cpg;
+    const float m0 = s_mean[g0], r0 = s_rstd[g0], m1 = s_mean[g1], r1 = s_rstd[g1];
+    float4 sc0, sh0, sc1, sh1;
+    sc0.x = r0 * ga0.x; sc0.y = r0 * ga0.y; sc0.z = r0 * ga0.z; sc0.w = r0 * ga0.w;
+    sc1.x = r1 * ga1.x; sc1.y = r1 * ga1.y; sc1.z = r1 * ga1.z; sc1.w = r1 * ga1.w;
+    sh0.x = fmaf(-m0, sc0.x, be0.x); sh0.y = fmaf(-m0, sc0.y, be0.y); sh0.z = fmaf(-m0, sc0.z, be0.z); sh0.w = fmaf(-m0, sc0.w, be0.w);
+    sh1.x = fmaf(-m1, sc1.x, be1.x); sh1.y = fmaf(-m1, sc1.y, be1.y); sh1.z = fmaf(-m1, sc1.z, be1.z); sh1.w = fmaf(-m1, sc1.w, be1.w);
+    const float4 y0 = norm_act(x0, sc0, sh0, k.silu);
+    const float4 y1 = norm_act(x1, sc1, sh1, k.silu);
+    const size_t o = pix * C + c;
+    if (k.outA) {
+      uint2 h0, l0, h1, l1;
+      split4(y0, h0, l0); split4(y1, h1, l1);
+      *reinterpret_cast<uint4*>(k.outA + o) = pack8(h0, h1);
+      *reinterpret_cast<uint4*>(k.outA + plane + o) = pack8(l0, l1);
+    }
+    if (k.outX) {
+      uint2 h0, l0, h1, l1;
+      split4(x0, h0, l0); split4(x1, h1, l1);
+      *reinterpret_cast<uint4*>(k.outX + o) = pack8(h0, h1);
+      *reinterpret_cast<uint4*>(k.outX + plane + o) = pack8(l0, l1);
+    }
+    if (k.outF) { *reinterpret_cast<float4*>(k.outF + o) = y0; *reinterpret_cast<float4*>(k.outF + o + 4) = y1; }
+    if (k.outXF) { *reinterpret_cast<float4*>(k.outXF + o) = x0; *reinterpret_cast<float4*>(k.outXF + o + 4) = x1; }
+  }
+}
+
 }  // namespace
 
 int gn_stats_max_blocks() { return 296; }
@@ -253,12 +325,14 @@ void launch_gn_prep(const PrepArgs& a, cudaStream_t s) {
   k.Ho = a.mode == kPrepDown ? a.H / 2 : (a.mode == kPrepUp ? a.H * 2 : a.H);
   k.Wo = a.mode == kPrepDown ? a.W / 2 : (a.mode == kPrepUp ? a.W * 2 : a.W);
   k.outA = a.outA; k.outX = a.outX; k.outF = a.outF; k.outXF = a.outXF;
-  const size_t total = static_cast<size_t>(k.Ho) * k.Wo * ((k.C1 + k.C2) / 4);
+  const bool plain8 = (a.mode == kPrepPlain) && (k.C1 % 8 == 0) && (k.C2 % 8 == 0);
+  const size_t total = static_cast<size_t>(k.Ho) * k.Wo * ((k.C1 + k.C2) / (plain8 ? 8 : 4));
   size_t blocks = (total + 255) / 256;
   const size_t cap = 148 * 16;
   if (blocks > cap) blocks = cap;
   dim3 grid(static_cast<unsigned>(blocks), a.B);
-  gn_prep_kernel<<<grid, 256, 0, s>>>(k);
+  if (plain8) gn_prep_plain8_kernel<<<grid, 256, 0, s>>>(k);
+  else gn_prep_kernel<<<grid, 256, 0, s>>>(k);
 }
 
 }  // namespace flowse

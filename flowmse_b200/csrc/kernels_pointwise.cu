@@ -74,8 +74,8 @@ inline unsigned grid_for(size_t n, int per_block = 256, unsigned cap = 148 * 8) 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
 temb_mlp_kernel(const TembWeights w, const float* __restrict__ t, float* __restrict__ temb_act) {
-  __shared__ float emb[256];
-  __shared__ float h1[512];
+  __shared__ __align__(16) float emb[256];
+  __shared__ __align__(16) float h1[512];
   const int b = blockIdx.x;
   const int j = threadIdx.x;
   if (j < 128) {
@@ -85,18 +85,34 @@ temb_mlp_kernel(const TembWeights w, const float* __restrict__ t, float* __restr
     emb[128 + j] = cosf(xp);
   }
   __syncthreads();
-  {
-    const float* row = w.l1_w + static_cast<size_t>(j) * 256;
+  // one warp per output row, lanes stride over the inputs (coalesced weight reads), 16 warps x 32 rows each
+  const int warp = j >> 5, lane = j & 31;
+  for (int r = warp; r < 512; r += 16) {
+    const float4* row = reinterpret_cast<const float4*>(w.l1_w + static_cast<size_t>(r) * 256);
     float acc = 0.f;
-    for (int i = 0; i < 256; ++i) acc = fmaf(row[i], emb[i], acc);
-    h1[j] = silu_f(acc + w.l1_b[j]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float4 wv = __ldg(row + lane + 32 * i);
+      const float4 x = *reinterpret_cast<const float4*>(&emb[4 * (lane + 32 * i)]);
+      acc = fmaf(wv.x, x.x, acc); acc = fmaf(wv.y, x.y, acc); acc = fmaf(wv.z, x.z, acc); acc = fmaf(wv.w, x.w, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) h1[r] = silu_f(acc + w.l1_b[r]);
   }
   __syncthreads();
-  {
-    const float* row = w.l2_w + static_cast<size_t>(j) * 512;
+  for (int r = warp; r < 512; r += 16) {
+    const float4* row = reinterpret_cast<const float4*>(w.l2_w + static_cast<size_t>(r) * 512);
     float acc = 0.f;
-    for (int i = 0; i < 512; ++i) acc = fmaf(row[i], h1[i], acc);
-    temb_act[static_cast<size_t>(b) * 512 + j] = silu_f(acc + w.l2_b[j]);   // act(temb), input of every Dense_0
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 wv = __ldg(row + lane + 32 * i);
+      const float4 x = *reinterpret_cast<const float4*>(&h1[4 * (lane + 32 * i)]);
+      acc = fmaf(wv.x, x.x, acc); acc = fmaf(wv.y, x.y, acc); acc = fmaf(wv.z, x.z, acc); acc = fmaf(wv.w, x.w, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) temb_act[static_cast<size_t>(b) * 512 + r] = silu_f(acc + w.l2_b[r]);   // act(temb), input of every Dense_0
   }
 }
 

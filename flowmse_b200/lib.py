@@ -48,6 +48,7 @@ def load_library():
     lib.flowse_kernel_launches.argtypes = [vp]; lib.flowse_kernel_launches.restype = ll
     lib.flowse_debug_tap.argtypes = [vp, i, C.POINTER(vp), C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     lib.flowse_debug_tap.restype = i
+    lib.flowse_profile_forward.argtypes = [vp, i, vp, vp, vp, vp, C.POINTER(i)]; lib.flowse_profile_forward.restype = i
     lib.flowse_debug_copy.argtypes = [vp, vp, vp, C.c_size_t]; lib.flowse_debug_copy.restype = i
     lib.flowse_pack_conv_weights.argtypes = [vp, i, i, i, vp, i, i, vp, C.POINTER(i)]
     lib.flowse_pack_conv_weights.restype = i
@@ -63,7 +64,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "flowse_create", "flowse_destroy", "flowse_last_error", "flowse_load_weights", "flowse_workspace_bytes",
     "flowse_prior_sample", "flowse_ncsnpp_forward", "flowse_euler_step", "flowse_sample", "flowse_set_option",
-    "flowse_kernel_launches", "flowse_debug_tap", "flowse_debug_copy", "flowse_pack_conv_weights", "flowse_op_gn_prep",
+    "flowse_kernel_launches", "flowse_profile_forward", "flowse_debug_tap", "flowse_debug_copy", "flowse_pack_conv_weights", "flowse_op_gn_prep",
     "flowse_op_conv_gemm", "flowse_op_attention",
 ]
 
@@ -199,6 +200,20 @@ class Context:
                                             float(sigma), out.data_ptr(), B, T, _stream()))
         return out
 
+    def profile_forward(self):
+        """Per-op device times of one network evaluation of the current plan: list of dicts
+        {kind, ms, flops, H, W, K, Cout}."""
+        import numpy as np
+        n_max = 4096
+        kinds = np.zeros(n_max, np.int32); ms = np.zeros(n_max, np.float32)
+        flops = np.zeros(n_max, np.float64); info = np.zeros(4 * n_max, np.int32)
+        n = C.c_int()
+        self._check(self._lib.flowse_profile_forward(self._h, n_max, kinds.ctypes.data, ms.ctypes.data,
+                                                     flops.ctypes.data, info.ctypes.data, C.byref(n)))
+        names = ["misc", "gn_stats", "gn_prep", "conv_gemm", "attention", "small", "temb"]
+        return [dict(kind=names[kinds[k]], ms=float(ms[k]), flops=float(flops[k]), H=int(info[4 * k]),
+                     W=int(info[4 * k + 1]), K=int(info[4 * k + 2]), Cout=int(info[4 * k + 3])) for k in range(n.value)]
+
     # ---- test hooks ----------------------------------------------------------------------------
     def debug_tap(self, module_idx: int, B: int) -> torch.Tensor:
         """Copy of all_modules[module_idx]'s output from the last forward, as NCHW fp32."""
@@ -244,12 +259,13 @@ class Context:
         return dict(A=A, X=X, F=Fo, XF=XF)
 
     def op_conv_gemm(self, A, Wp, wexp, bias, cout, ntaps=9, X=None, residual=None, div_sqrt2=False, impl=0,
-                     bias_bstride=0):
+                     bias_bstride=0, out=None):
         """A: fp16 [2,B,H,W,Cin]; Wp: fp16 [2,Npad,K]; returns NHWC fp32 [B,H,W,cout]."""
         _, B, H, W, Cin = A.shape
         Cin2 = 0 if X is None else X.shape[4]
         npad = Wp.shape[1]
-        out = torch.zeros((B, H, W, cout), dtype=torch.float32, device=A.device)
+        if out is None:
+            out = torch.zeros((B, H, W, cout), dtype=torch.float32, device=A.device)
         self._check(self._lib.flowse_op_conv_gemm(self._h, A.data_ptr(), Cin, ntaps, _ptr(X), Cin2, Wp.data_ptr(), npad,
                                                   wexp, bias.data_ptr(), bias_bstride, _ptr(residual), int(div_sqrt2),
                                                   out.data_ptr(), cout, cout, B, H, W, impl, _stream()))
