@@ -72,6 +72,11 @@ struct GemmParams {
   float* out;
   int div_sqrt2;
   long long* dbg;   // optional per-CTA phase timestamps (FLOWSE_CONV_DBG=1), else null
+  // split-K (low-resolution layers: few output tiles, long K): blockIdx.z owns a contiguous range of K blocks and
+  // writes its raw partial tile to partial[z][pixel][ldc]; splitk_reduce_kernel applies the epilogue.
+  int ksplit;
+  float* partial;
+  long long partial_plane;   // elements per split = B*H*W*ldc
 };
 
 template <int BN>
@@ -92,7 +97,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   auto stamp = [&](int slot) { if (p.dbg) p.dbg[static_cast<size_t>(cta_lin) * 8 + slot] = static_cast<long long>(ptx::globaltimer_ns()); };
   if (threadIdx.x == 0) stamp(0);
 
@@ -106,7 +111,10 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int n0 = blockIdx.y * BN;
 
   const int nkb_main = p.ntaps * p.nchunk_main;
-  const int nkb = nkb_main + p.nchunk_sc;
+  const int nkb_total = nkb_main + p.nchunk_sc;
+  const int kb_begin = (p.ksplit > 1) ? static_cast<int>((static_cast<long long>(blockIdx.z) * nkb_total) / p.ksplit) : 0;
+  const int kb_end = (p.ksplit > 1) ? static_cast<int>((static_cast<long long>(blockIdx.z + 1) * nkb_total) / p.ksplit)
+                                    : nkb_total;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -134,7 +142,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sA_hi = smem_base + stage * C::STAGE_BYTES;
         const uint32_t sA_lo = sA_hi + A_BYTES;
@@ -164,10 +172,10 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       constexpr uint32_t idesc = ptx::make_idesc_f16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
-        if (kb == 0) stamp(2);
+        if (kb == kb_begin) stamp(2);
         const uint32_t sA_hi = smem_base + stage * C::STAGE_BYTES;
         const uint32_t sA_lo = sA_hi + A_BYTES;
         const uint32_t sB_hi = sA_lo + A_BYTES;
@@ -179,7 +187,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);   // 32 B per K step
-          const int ks = kb * (BK / UMMA_K) + k;
+          const int ks = (kb - kb_begin) * (BK / UMMA_K) + k;   // K step index local to this CTA
           const uint32_t d_main = tmem_acc + static_cast<uint32_t>((ks % kMainSlots) * C::SLOT_COLS);
           const uint32_t d_corr = tmem_acc + static_cast<uint32_t>(kMainSlots * C::SLOT_COLS);
           ptx::mma_f16_ss(d_main, dA_hi + koff, dB_hi + koff, idesc, ks >= kMainSlots ? 1u : 0u);
@@ -230,7 +238,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
       for (int it = 0; it < NIT; ++it) {
         res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.residual && off[it] >= 0 && n0 + col_base + c0 + cj < p.Cout)
+        if (p.residual && !p.partial && off[it] >= 0 && n0 + col_base + c0 + cj < p.Cout)
           res[it] = __ldg(reinterpret_cast<const float4*>(p.residual + off[it] + c0));
       }
     };
@@ -271,7 +279,19 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
         for (int it = 0; it < NIT; ++it) cur[it] = res[it];
         if (ci + 1 < NCHUNK) load_res(c0 + CH);        // next pass's residual block in flight during this one
-        if (n < p.Cout) {
+        if (p.partial) {
+          if (n < p.Cout) {
+            float* dst = p.partial + static_cast<long long>(blockIdx.z) * p.partial_plane;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+              if (off[it] >= 0) {
+                const float4 a = *reinterpret_cast<const float4*>(stg + (it * RPI + sub_row) * C::STG_STRIDE + cj);
+                *reinterpret_cast<float4*>(dst + off[it] + c0) =
+                    make_float4(a.x * p.wscale_inv, a.y * p.wscale_inv, a.z * p.wscale_inv, a.w * p.wscale_inv);
+              }
+            }
+          }
+        } else if (n < p.Cout) {
           const float4 bv = __ldg(reinterpret_cast<const float4*>(brow + n));
 #pragma unroll
           for (int it = 0; it < NIT; ++it) {
@@ -298,6 +318,29 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     ptx::tmem_dealloc(tmem_acc, C::TMEM_COLS);
   }
   if (threadIdx.x == 32) stamp(5);
+}
+
+// out = epilogue(sum_z partial[z]) for split-K launches; fixed summation order (deterministic).
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int S, long long plane, const float* __restrict__ bias,
+                     int bias_bstride, const float* __restrict__ residual, float post, float* __restrict__ out,
+                     long long n4, int ldc4, long long hw_ldc4) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 acc = __ldcg(reinterpret_cast<const float4*>(partial) + i);
+  for (int z = 1; z < S; ++z) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + z * plane) + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const int n = static_cast<int>(i % ldc4) * 4;
+  const int b = static_cast<int>(i / hw_ldc4);
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + static_cast<size_t>(b) * bias_bstride + n));
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (residual) r = __ldg(reinterpret_cast<const float4*>(residual) + i);
+  float4 v;
+  v.x = (acc.x + bv.x + r.x) * post; v.y = (acc.y + bv.y + r.y) * post;
+  v.z = (acc.z + bv.z + r.z) * post; v.w = (acc.w + bv.w + r.w) * post;
+  reinterpret_cast<float4*>(out)[i] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -439,6 +482,7 @@ GemmParams make_params(const ConvGemmArgs& a) {
   p.out = a.out;
   p.div_sqrt2 = a.div_sqrt2;
   p.dbg = nullptr;
+  p.ksplit = 1; p.partial = nullptr; p.partial_plane = 0;
   return p;
 }
 
@@ -472,11 +516,23 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   else tmX = tmA;
   if (!make_w_map(&tmW, a.Wp, a.Npad, K, BN, err)) return 1;
   dim3 grid(a.B * p.tiles_w * p.tiles_h, (a.Cout + BN - 1) / BN);
+  // split-K when the output has too few tiles to fill the GPU (needs ldc == Cout so partial planes are dense)
+  const int tiles = grid.x * grid.y;
+  const int nkb_total = a.ntaps * (a.Cin / BK) + (a.X ? a.Cin2 / BK : 0);
+  int S = 1;
+  if (a.splitk_scratch && tiles <= 74 && a.ldc == a.Cout) {
+    S = std::min(148 / tiles, nkb_total / 4);
+    const long long plane = static_cast<long long>(a.B) * a.H * a.W * a.ldc;
+    while (S > 1 && static_cast<size_t>(S) * plane > a.splitk_scratch_elems) --S;
+    if (S < 2) S = 1;
+    if (S > 1) { p.ksplit = S; p.partial = a.splitk_scratch; p.partial_plane = plane; grid.z = S; }
+  }
   static const bool dbg = getenv("FLOWSE_CONV_DBG") != nullptr;
   long long* dbuf = nullptr;
   const size_t ncta = static_cast<size_t>(grid.x) * grid.y;
   if (dbg) { cudaMalloc(&dbuf, ncta * 8 * sizeof(long long)); cudaMemset(dbuf, 0, ncta * 8 * sizeof(long long)); p.dbg = dbuf; }
   conv_gemm_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(tmA, tmX, tmW, p);
+  ++launch_counter();
   if (dbg) {
     cudaStreamSynchronize(s);
     std::vector<long long> h(ncta * 8);
@@ -491,6 +547,13 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
     fprintf(stderr, "[conv dbg] ctas=%zu kb=%d  setup %.2f us | first-data %.2f | mainloop %.2f | epilogue %.2f | teardown %.2f | kernel span %.2f us\n",
             ncta, p.ntaps * p.nchunk_main + p.nchunk_sc, ph[0] / ncta / 1e3, ph[1] / ncta / 1e3, ph[2] / ncta / 1e3,
             ph[3] / ncta / 1e3, ph[4] / ncta / 1e3, (tmax - tmin) / 1e3);
+  }
+  if (S > 1) {
+    const long long n4 = p.partial_plane / 4;
+    splitk_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(
+        p.partial, S, p.partial_plane, a.bias, a.bias_bstride, a.residual, a.div_sqrt2 ? 0.70710678118654752440f : 1.0f,
+        a.out, n4, a.ldc / 4, static_cast<long long>(a.H) * a.W * a.ldc / 4);
+    ++launch_counter();
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv_gemm launch: ") + cudaGetErrorString(e); return 1; }
@@ -514,6 +577,7 @@ int launch_conv_gemm_simt(const ConvGemmArgs& a, cudaStream_t s, std::string* er
   const int threads = std::min(128, ((a.Cout + 31) / 32) * 32);
   dim3 grid(static_cast<unsigned>(static_cast<size_t>(a.B) * a.H * a.W), (a.Cout + threads - 1) / threads);
   conv_gemm_simt_kernel<<<grid, threads, 0, s>>>(a.A, a.X, a.Wp, a.Cin, a.X ? a.Cin2 : 0, a.ntaps, a.Npad, K, p, a.B);
+  ++launch_counter();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv_gemm_simt launch: ") + cudaGetErrorString(e); return 1; }
   return 0;

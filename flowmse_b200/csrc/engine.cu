@@ -157,12 +157,14 @@ struct flowse_ctx {
   // options
   int conv_impl = 0;
   int use_graph = 1;
-  long long launches = 0;
+  long long graph_kernels = 0;      // kernels executed through graph replays (not seen by launch_counter)
+  long long counter_base = 0;
   std::unique_ptr<Plan> plan;
   cudaStream_t cap_stream = nullptr;   // capture happens here: the caller's stream may be the legacy default stream
   // scratch for op-level entry points
   double* op_stats = nullptr; double* op_partials = nullptr; unsigned* op_counters = nullptr;
   float* op_scratch = nullptr; size_t op_scratch_bytes = 0;
+  float* op_splitk = nullptr;
 };
 
 namespace {
@@ -335,7 +337,7 @@ struct Builder {
   // scratch
   __half *scrA = nullptr, *scrX = nullptr;
   float *scrH1 = nullptr, *scrF = nullptr, *scrQKV = nullptr, *scrS = nullptr, *scrO = nullptr, *scrHead = nullptr;
-  float *temb_act = nullptr, *bias_table = nullptr;
+  float *temb_act = nullptr, *bias_table = nullptr, *splitk = nullptr;
 
   void push(int nk, std::function<int(cudaStream_t)> fn, int kind = 0, double flops = 0.0, int i0 = 0, int i1 = 0,
             int i2 = 0, int i3 = 0) {
@@ -380,7 +382,8 @@ struct Builder {
     c0.wscale_inv = r.conv0.wscale_inv; c0.bias = bias_table + r.dense_off; c0.bias_bstride = ctx->dense_rows;
     c0.residual = nullptr; c0.div_sqrt2 = 0; c0.out = scrH1; c0.Cout = r.cout; c0.ldc = r.cout;
     c0.B = B; c0.H = Ho; c0.W = Wo;
-    { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c0, s); }, 3, conv_flops(c0), c0.H, c0.W, c0.ntaps * c0.Cin + (c0.X ? c0.Cin2 : 0), c0.Cout); }
+    c0.splitk_scratch = splitk; c0.splitk_scratch_elems = kSplitKScratchElems;
+    { flowse_ctx* cx = ctx; push(2, [=](cudaStream_t s) { return run_conv(cx, c0, s); }, 3, conv_flops(c0), c0.H, c0.W, c0.ntaps * c0.Cin + (c0.X ? c0.Cin2 : 0), c0.Cout); }
     float* h1 = scrH1; const int Co = r.cout;
     push(1, [=](cudaStream_t s) { launch_gn_stats(h1, Co, nullptr, 0, Bc, Ho * Wo, st1, gp, gc, s); return 0; }, 1);
     PrepArgs pb{};
@@ -392,7 +395,8 @@ struct Builder {
     c1.Wp = r.conv1.wp; c1.Npad = r.conv1.Npad; c1.wscale_inv = r.conv1.wscale_inv; c1.bias = r.bias1;
     c1.bias_bstride = 0; c1.residual = r.has_sc ? nullptr : s1; c1.div_sqrt2 = 1; c1.out = out.p; c1.Cout = Co;
     c1.ldc = Co; c1.B = B; c1.H = Ho; c1.W = Wo;
-    { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c1, s); }, 3, conv_flops(c1), c1.H, c1.W, c1.ntaps * c1.Cin + (c1.X ? c1.Cin2 : 0), c1.Cout); }
+    c1.splitk_scratch = splitk; c1.splitk_scratch_elems = kSplitKScratchElems;
+    { flowse_ctx* cx = ctx; push(2, [=](cudaStream_t s) { return run_conv(cx, c1, s); }, 3, conv_flops(c1), c1.H, c1.W, c1.ntaps * c1.Cin + (c1.X ? c1.Cin2 : 0), c1.Cout); }
     plan->taps[mi] = out;
     return out;
   }
@@ -457,6 +461,7 @@ struct Builder {
     scrS = ar.alloc<float>(static_cast<size_t>(B) * La * La);
     scrO = ar.alloc<float>(static_cast<size_t>(B) * La * 256);
     scrHead = ar.alloc<float>(top * 4);
+    splitk = ar.alloc<float>(kSplitKScratchElems);
     plan->stats_bytes = static_cast<size_t>(128) * B * kGroups * 2 * sizeof(double);
     plan->stats = ar.alloc<double>(plan->stats_bytes / sizeof(double));
 
@@ -526,7 +531,8 @@ struct Builder {
         ConvGemmArgs c{};
         c.A = scrA; c.Cin = C; c.ntaps = 9; c.Wp = hw.conv.wp; c.Npad = hw.conv.Npad; c.wscale_inv = hw.conv.wscale_inv;
         c.bias = hw.bias; c.bias_bstride = 0; c.out = scrHead; c.Cout = 4; c.ldc = 4; c.B = B; c.H = Hh; c.W = Ww;
-        { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c, s); }, 3, conv_flops(c), c.H, c.W, c.ntaps * c.Cin + (c.X ? c.Cin2 : 0), c.Cout); }
+        c.splitk_scratch = splitk; c.splitk_scratch_elems = kSplitKScratchElems;
+        { flowse_ctx* cx = ctx; push(2, [=](cudaStream_t s) { return run_conv(cx, c, s); }, 3, conv_flops(c), c.H, c.W, c.ntaps * c.Cin + (c.X ? c.Cin2 : 0), c.Cout); }
         float4* pyr = ar.alloc<float4>(static_cast<size_t>(B) * Hh * Ww);
         const float4* prev = pyr_prev; const float4* head = reinterpret_cast<const float4*>(scrHead);
         push(1, [=](cudaStream_t s) { launch_pyr_accum(prev, head, pyr, Bc, Hh, Ww, s); return 0; }, 5);
@@ -592,7 +598,10 @@ int run_backbone(flowse_ctx* ctx, cudaStream_t s) {
       cudaGraph_t g = nullptr;
       if (!ctx->cap_stream) CK(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
       CK(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
+      const long long c0 = launch_counter();
       const int rc = run_ops(ctx, ctx->cap_stream);
+      p->kernels_per_forward = static_cast<int>(launch_counter() - c0);
+      ctx->counter_base += p->kernels_per_forward;    // captured, not executed
       cudaError_t e = cudaStreamEndCapture(ctx->cap_stream, &g);
       if (rc) { if (g) cudaGraphDestroy(g); return rc; }
       if (e != cudaSuccess) { ctx->err = std::string("graph capture: ") + cudaGetErrorString(e); return 1; }
@@ -602,18 +611,17 @@ int run_backbone(flowse_ctx* ctx, cudaStream_t s) {
       p->graph_ready = true;
     }
     CK(cudaGraphLaunch(p->graph_fwd, s));
+    ctx->graph_kernels += p->kernels_per_forward;
   } else {
     if (int rc = run_ops(ctx, s)) return rc;
     ++p->eager_runs;
   }
-  ctx->launches += p->kernels_per_forward;
   return 0;
 }
 
 int final_op(flowse_ctx* ctx, int mode, const float2* xin, float2* out, cudaStream_t s) {
   Plan* p = ctx->plan.get();
   launch_final(p->pyr_out, p->t_dev, ctx->out_w, ctx->out_b, xin, p->step_dev, out, mode, p->B, kImage * p->T, s);
-  ctx->launches += 1;
   return 0;
 }
 
@@ -621,7 +629,6 @@ int set_t(flowse_ctx* ctx, float t, float step, cudaStream_t s) {
   // t and the step size travel as kernel arguments: no host buffer, no stream synchronisation
   Plan* p = ctx->plan.get();
   launch_set_scalars(p->t_dev, p->B, t, p->step_dev, step, s);
-  ctx->launches += 1;
   return 0;
 }
 
@@ -653,6 +660,7 @@ int flowse_create(flowse_ctx** out, int device) {
   flowse_ctx* ctx = new flowse_ctx();
   ctx->device = device;
   ctx->mods = build_modules();
+  ctx->counter_base = launch_counter();
   cudaSetDevice(device);
   *out = ctx;
   return 0;
@@ -672,6 +680,7 @@ void flowse_destroy(flowse_ctx* ctx) {
   if (ctx->op_partials) cudaFree(ctx->op_partials);
   if (ctx->op_counters) cudaFree(ctx->op_counters);
   if (ctx->op_scratch) cudaFree(ctx->op_scratch);
+  if (ctx->op_splitk) cudaFree(ctx->op_splitk);
   delete ctx;
 }
 
@@ -707,7 +716,6 @@ int flowse_prior_sample(flowse_ctx* ctx, const void* y, const void* z, float sig
   if (n <= 0) return 0;
   launch_prior(static_cast<const float2*>(y), static_cast<const float2*>(z), sigma, static_cast<float2*>(x),
                static_cast<size_t>(n), static_cast<cudaStream_t>(stream));
-  ctx->launches += 1;
   CK(cudaGetLastError());
   return 0;
 }
@@ -719,7 +727,6 @@ int flowse_euler_step(flowse_ctx* ctx, const void* x, const void* v, float steps
   if (n <= 0) return 0;
   launch_euler_update(static_cast<const float2*>(x), static_cast<const float2*>(v), -stepsize,
                       static_cast<float2*>(x_out), static_cast<size_t>(n), static_cast<cudaStream_t>(stream));
-  ctx->launches += 1;
   CK(cudaGetLastError());
   return 0;
 }
@@ -756,7 +763,6 @@ int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const voi
   CK(cudaMemcpyAsync(p->y, y, n * sizeof(float2), cudaMemcpyDeviceToDevice, s));
   launch_prior(y_prior ? static_cast<const float2*>(y_prior) : p->y, static_cast<const float2*>(z), sigma, p->x, n,
                s);                                                          // x_T = y_prior + sigma z
-  ctx->launches += 1;
   for (int i = 0; i < N; ++i) {
     const float t = ts[i];
     const float step = (i != N - 1) ? (t - ts[i + 1]) : ts[N - 1];        // fp32, as sampling/__init__.py:50-53
@@ -776,7 +782,6 @@ int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const voi
       if (int rc = run_backbone(ctx, s)) return rc;
       final_op(ctx, 1, nullptr, p->vb, s);                                  // vb = VF(x_next, t+dt)
       launch_heun_combine(p->xa, p->va, p->vb, dt / 2, p->x, n, s);
-      ctx->launches += 2;
     } else {
       // x = x + dt VF(x + dt/2 VF(x,t), t + dt/2)
       const float dt = -step;
@@ -788,7 +793,6 @@ int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const voi
       if (int rc = run_backbone(ctx, s)) return rc;
       final_op(ctx, 1, nullptr, p->vb, s);
       launch_axpy_c(p->xa, p->vb, dt, p->x, n, s);
-      ctx->launches += 2;
     }
   }
   CK(cudaMemcpyAsync(x_out, p->x, n * sizeof(float2), cudaMemcpyDeviceToDevice, s));
@@ -823,7 +827,6 @@ int flowse_profile_forward(flowse_ctx* ctx, int max_ops, int* kinds, float* ms, 
   *n_ops = n;
   for (auto& e : ev) cudaEventDestroy(e);
   cudaStreamDestroy(s);
-  ctx->launches += p->kernels_per_forward;
   return 0;
 }
 
@@ -843,7 +846,9 @@ int flowse_set_option(flowse_ctx* ctx, const char* key, int value) {
   return 0;
 }
 
-long long flowse_kernel_launches(const flowse_ctx* ctx) { return ctx ? ctx->launches : 0; }
+long long flowse_kernel_launches(const flowse_ctx* ctx) {
+  return ctx ? (launch_counter() - ctx->counter_base + ctx->graph_kernels) : 0;
+}
 
 int flowse_debug_tap(flowse_ctx* ctx, int module_idx, const float** ptr, int* C, int* H, int* W) {
   if (!ctx) return 2;
@@ -898,7 +903,6 @@ int flowse_op_gn_prep(flowse_ctx* ctx, const float* src1, int C1, const float* s
   pa.B = B; pa.H = H; pa.W = W; pa.mode = mode; pa.silu = silu;
   pa.outA = static_cast<__half*>(outA); pa.outX = static_cast<__half*>(outX); pa.outF = outF; pa.outXF = outXF;
   launch_gn_prep(pa, s);
-  ctx->launches += 2;
   CK(cudaGetLastError());
   return 0;
 }
@@ -913,11 +917,12 @@ int flowse_op_conv_gemm(flowse_ctx* ctx, const void* A, int Cin, int ntaps, cons
   a.Wp = static_cast<const __half*>(Wp); a.Npad = Npad; a.wscale_inv = std::ldexp(1.0f, -wexp); a.bias = bias;
   a.bias_bstride = bias_bstride; a.residual = residual; a.div_sqrt2 = div_sqrt2; a.out = out; a.Cout = Cout; a.ldc = ldc;
   a.B = B; a.H = H; a.W = W;
+  if (!ctx->op_splitk) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_splitk), kSplitKScratchElems * sizeof(float)));
+  a.splitk_scratch = ctx->op_splitk; a.splitk_scratch_elems = kSplitKScratchElems;
   std::string e;
   const int rc = impl == 1 ? launch_conv_gemm_simt(a, static_cast<cudaStream_t>(stream), &e)
                            : launch_conv_gemm(a, static_cast<cudaStream_t>(stream), &e);
   if (rc) ctx->err = e;
-  ctx->launches += 1;
   return rc;
 }
 
@@ -934,6 +939,7 @@ int flowse_op_attention(flowse_ctx* ctx, int module_idx, const float* x, float* 
   if (ctx->op_scratch_bytes < need) {
     CK(cudaDeviceSynchronize());
     if (ctx->op_scratch) cudaFree(ctx->op_scratch);
+  if (ctx->op_splitk) cudaFree(ctx->op_splitk);
     CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_scratch), need));
     ctx->op_scratch_bytes = need;
   }
@@ -967,7 +973,6 @@ int flowse_op_attention(flowse_ctx* ctx, int module_idx, const float* x, float* 
   g.A = O; g.lda = C; g.Bm = a.w3; g.ldb = C; g.C = out; g.ldc = C; g.M = B * L; g.N = C; g.K = C; g.batch = 1;
   g.alpha = 1.f; g.bias = a.b3; g.residual = x; g.ldr = C; g.div_sqrt2 = 1;
   launch_sgemm(g, s);
-  ctx->launches += 7;
   CK(cudaGetLastError());
   return 0;
 }

@@ -8,6 +8,9 @@
 
 namespace flowse {
 
+// Process-wide count of kernel launches issued by this library (incremented by every launch_* helper).
+long long& launch_counter();
+
 constexpr int kGroups = 32;          // GroupNorm groups: min(C/4, 32) == 32 for every C in the net (layerspp.py:219)
 constexpr float kGnEps = 1e-6f;
 constexpr float kSqrt2 = 1.41421356237309504880f;   // np.sqrt(2.) rounded to fp32 (layerspp.py:274)
@@ -107,7 +110,10 @@ struct ConvGemmArgs {
   int Cout;             // valid output channels (<= Npad)
   int ldc;
   int B, H, W;
+  float* splitk_scratch;        // optional fp32 scratch enabling split-K for low-resolution layers (may be null)
+  size_t splitk_scratch_elems;
 };
+constexpr size_t kSplitKScratchElems = static_cast<size_t>(148) * 128 * 128;   // enough for any one-wave split
 // returns 0 on success; fills err otherwise.
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t s, std::string* err);
 // Slow SIMT evaluation of exactly the same operands (debug / cross-check only; never on the product path).

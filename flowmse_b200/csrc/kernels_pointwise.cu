@@ -4,6 +4,11 @@
 
 namespace flowse {
 
+long long& launch_counter() {
+  static long long n = 0;
+  return n;
+}
+
 namespace {
 
 constexpr float kPiF = 3.14159274101257324219f;   // np.pi rounded to fp32 (scalar * fp32 tensor, layerspp.py:40)
@@ -358,18 +363,21 @@ softmax_rows_kernel(float* __restrict__ s, int rows, int cols) {
 
 void launch_set_scalars(float* t_dev, int B, float t, float* step_dev, float step, cudaStream_t s) {
   set_scalars_kernel<<<(B + 127) / 128, 128, 0, s>>>(t_dev, B, t, step_dev, step);
+  ++launch_counter();
 }
 
 void launch_prior(const float2* y, const float2* z, float sigma, float2* x, size_t n, cudaStream_t s) {
   const size_t n4 = n / 2;
   prior_kernel<<<grid_for(n4), 256, 0, s>>>(reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(z),
                                             sigma, reinterpret_cast<float4*>(x), n4, y, z, x, n);
+  ++launch_counter();
 }
 
 void launch_axpy_c(const float2* a, const float2* b, float c, float2* out, size_t n, cudaStream_t s) {
   const size_t n4 = n / 2;
   axpy_kernel<<<grid_for(n4), 256, 0, s>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), c,
                                            reinterpret_cast<float4*>(out), n4, a, b, out, n);
+  ++launch_counter();
 }
 
 void launch_euler_update(const float2* x, const float2* v, float dt, float2* out, size_t n, cudaStream_t s) {
@@ -379,45 +387,54 @@ void launch_euler_update(const float2* x, const float2* v, float dt, float2* out
 void launch_heun_combine(const float2* x, const float2* v0, const float2* v1, float c, float2* out, size_t n,
                          cudaStream_t s) {
   heun_kernel<<<grid_for(n), 256, 0, s>>>(x, v0, v1, c, out, n);
+  ++launch_counter();
 }
 
 void launch_temb(const TembWeights& w, const float* t, int B, float* temb_act, float* bias_table, cudaStream_t s) {
   temb_mlp_kernel<<<B, 512, 0, s>>>(w, t, temb_act);
+  ++launch_counter();
   const int warps_per_block = 8;
   temb_dense_kernel<<<(w.R + warps_per_block - 1) / warps_per_block, 256, 0, s>>>(w.dense_w, w.dense_b, temb_act, w.R,
                                                                                   B, bias_table);
+  ++launch_counter();
 }
 
 void launch_conv_in(const float2* x, const float2* y, const float* w, const float* bias, float* out, float4* pyr,
                     int B, int H, int W, cudaStream_t s) {
   dim3 grid((W + 31) / 32, (H + 3) / 4, B);
   conv_in_kernel<<<grid, 256, 0, s>>>(x, y, w, bias, out, pyr, H, W);
+  ++launch_counter();
 }
 
 void launch_fir_down4(const float4* in, float4* out, int B, int H, int W, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * H * W;
   fir_down4_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out, B, H, W);
+  ++launch_counter();
 }
 
 void launch_combine(const float* h, const float4* pyr, const float* w, const float* b, float* out, int B, int H,
                     int W, int C, cudaStream_t s) {
   const size_t npix = static_cast<size_t>(B) * H * W;
   combine_kernel<<<grid_for(npix * (C / 4)), 256, 0, s>>>(h, pyr, w, b, out, npix, C);
+  ++launch_counter();
 }
 
 void launch_pyr_accum(const float4* prev, const float4* head, float4* out, int B, int H, int W, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * H * W;
   pyr_accum_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(prev, head, out, B, H, W);
+  ++launch_counter();
 }
 
 void launch_final(const float4* pyr, const float* t, const float* wo, const float* bo, const float2* xin,
                   const float* stepsize_dev, float2* out, int mode, int B, int HW, cudaStream_t s) {
   final_kernel<<<grid_for(static_cast<size_t>(B) * HW), 256, 0, s>>>(pyr, t, wo, bo, xin, stepsize_dev, out, mode, B,
                                                                       HW);
+  ++launch_counter();
 }
 
 void launch_softmax_rows(float* sm, int rows, int cols, cudaStream_t st) {
   softmax_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(sm, rows, cols);
+  ++launch_counter();
 }
 
 }  // namespace flowse
