@@ -74,6 +74,7 @@ struct GemmParams {
   long long* dbg;   // optional per-CTA phase timestamps (FLOWSE_CONV_DBG=1), else null
   // split-K (low-resolution layers: few output tiles, long K): blockIdx.z owns a contiguous range of K blocks and
   // writes its raw partial tile to partial[z][pixel][ldc]; splitk_reduce_kernel applies the epilogue.
+  double* qstats;    // optional quad statistics of the output: [B][Cout/4] x {sum, sumsq}, accumulated with fp64 atomics
   int ksplit;
   float* partial;
   long long partial_plane;   // elements per split = B*H*W*ldc
@@ -293,6 +294,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         } else if (n < p.Cout) {
           const float4 bv = __ldg(reinterpret_cast<const float4*>(brow + n));
+          float qs_s = 0.f, qs_q = 0.f;
 #pragma unroll
           for (int it = 0; it < NIT; ++it) {
             if (off[it] >= 0) {
@@ -303,6 +305,21 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               v.z = (a.z * p.wscale_inv + bv.z + cur[it].z) * post;
               v.w = (a.w * p.wscale_inv + bv.w + cur[it].w) * post;
               *reinterpret_cast<float4*>(p.out + off[it] + c0) = v;
+              qs_s += (v.x + v.y) + (v.z + v.w);
+              qs_q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            }
+          }
+          if (p.qstats) {
+            // lanes sharing lane % LPR hold the same channel quad: fold the RPI row-lanes, then one fp64 atomic pair
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) {
+              qs_s += __shfl_xor_sync(0xffffffffu, qs_s, o);
+              qs_q += __shfl_xor_sync(0xffffffffu, qs_q, o);
+            }
+            if (sub_row == 0) {
+              double* dst = p.qstats + (static_cast<size_t>(b) * (p.Cout >> 2) + (n >> 2)) * 2;
+              atomicAdd(dst, static_cast<double>(qs_s));
+              atomicAdd(dst + 1, static_cast<double>(qs_q));
             }
           }
         }
@@ -320,27 +337,44 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (threadIdx.x == 32) stamp(5);
 }
 
-// out = epilogue(sum_z partial[z]) for split-K launches; fixed summation order (deterministic).
+// out = epilogue(sum_z partial[z]) for split-K launches; fixed summation order (deterministic).  grid = (blocks, B).
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int S, long long plane, const float* __restrict__ bias,
                      int bias_bstride, const float* __restrict__ residual, float post, float* __restrict__ out,
-                     long long n4, int ldc4, long long hw_ldc4) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  float4 acc = __ldcg(reinterpret_cast<const float4*>(partial) + i);
-  for (int z = 1; z < S; ++z) {
-    const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + z * plane) + i);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                     int n4_per_batch, int ldc4, double* __restrict__ qstats) {
+  __shared__ float ss[256], sq[256];
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  float ls = 0.f, lq = 0.f;
+  if (j < n4_per_batch) {
+    const long long i = static_cast<long long>(b) * n4_per_batch + j;
+    float4 acc = __ldcg(reinterpret_cast<const float4*>(partial) + i);
+    for (int z = 1; z < S; ++z) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + z * plane) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const int n = (j % ldc4) * 4;
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + static_cast<size_t>(b) * bias_bstride + n));
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (residual) r = __ldg(reinterpret_cast<const float4*>(residual) + i);
+    float4 v;
+    v.x = (acc.x + bv.x + r.x) * post; v.y = (acc.y + bv.y + r.y) * post;
+    v.z = (acc.z + bv.z + r.z) * post; v.w = (acc.w + bv.w + r.w) * post;
+    reinterpret_cast<float4*>(out)[i] = v;
+    ls = (v.x + v.y) + (v.z + v.w);
+    lq = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
   }
-  const int n = static_cast<int>(i % ldc4) * 4;
-  const int b = static_cast<int>(i / hw_ldc4);
-  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + static_cast<size_t>(b) * bias_bstride + n));
-  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (residual) r = __ldg(reinterpret_cast<const float4*>(residual) + i);
-  float4 v;
-  v.x = (acc.x + bv.x + r.x) * post; v.y = (acc.y + bv.y + r.y) * post;
-  v.z = (acc.z + bv.z + r.z) * post; v.w = (acc.w + bv.w + r.w) * post;
-  reinterpret_cast<float4*>(out)[i] = v;
+  if (qstats) {            // block covers 256 / ldc4 pixels x ldc4 quads (256 % ldc4 == 0, rows block-aligned)
+    ss[threadIdx.x] = ls; sq[threadIdx.x] = lq;
+    __syncthreads();
+    if (threadIdx.x < ldc4) {
+      float as = 0.f, aq = 0.f;
+      for (int t = threadIdx.x; t < 256; t += ldc4) { as += ss[t]; aq += sq[t]; }
+      double* dst = qstats + (static_cast<size_t>(b) * ldc4 + threadIdx.x) * 2;
+      atomicAdd(dst, static_cast<double>(as));
+      atomicAdd(dst + 1, static_cast<double>(aq));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -387,6 +421,11 @@ __global__ void conv_gemm_simt_kernel(const __half* __restrict__ A, const __half
   if (p.residual) v += p.residual[pix * p.ldc + n];
   if (p.div_sqrt2) v = __fdiv_rn(v, kSqrt2);
   p.out[pix * p.ldc + n] = v;
+  if (p.qstats) {      // debug path: one fp64 atomic pair per element
+    double* dst = p.qstats + (static_cast<size_t>(b) * (p.Cout >> 2) + (n >> 2)) * 2;
+    atomicAdd(dst, static_cast<double>(v));
+    atomicAdd(dst + 1, static_cast<double>(v) * static_cast<double>(v));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -483,6 +522,7 @@ GemmParams make_params(const ConvGemmArgs& a) {
   p.div_sqrt2 = a.div_sqrt2;
   p.dbg = nullptr;
   p.ksplit = 1; p.partial = nullptr; p.partial_plane = 0;
+  p.qstats = a.qstats;
   return p;
 }
 
@@ -520,7 +560,7 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   const int tiles = grid.x * grid.y;
   const int nkb_total = a.ntaps * (a.Cin / BK) + (a.X ? a.Cin2 / BK : 0);
   int S = 1;
-  if (a.splitk_scratch && tiles <= 74 && a.ldc == a.Cout) {
+  if (a.splitk_scratch && tiles <= 74 && a.ldc == a.Cout && (!a.qstats || 256 % (a.ldc / 4) == 0)) {
     S = std::min(148 / tiles, nkb_total / 4);
     const long long plane = static_cast<long long>(a.B) * a.H * a.W * a.ldc;
     while (S > 1 && static_cast<size_t>(S) * plane > a.splitk_scratch_elems) --S;
@@ -549,10 +589,12 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
             ph[3] / ncta / 1e3, ph[4] / ncta / 1e3, (tmax - tmin) / 1e3);
   }
   if (S > 1) {
-    const long long n4 = p.partial_plane / 4;
-    splitk_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(
-        p.partial, S, p.partial_plane, a.bias, a.bias_bstride, a.residual, a.div_sqrt2 ? 0.70710678118654752440f : 1.0f,
-        a.out, n4, a.ldc / 4, static_cast<long long>(a.H) * a.W * a.ldc / 4);
+    const int n4b = a.H * a.W * a.ldc / 4;
+    const bool can_stats = a.qstats && (256 % (a.ldc / 4) == 0);
+    dim3 rgrid((n4b + 255) / 256, a.B);
+    splitk_reduce_kernel<<<rgrid, 256, 0, s>>>(p.partial, S, p.partial_plane, a.bias, a.bias_bstride, a.residual,
+                                               a.div_sqrt2 ? 0.70710678118654752440f : 1.0f, a.out, n4b, a.ldc / 4,
+                                               can_stats ? a.qstats : nullptr);
     ++launch_counter();
   }
   cudaError_t e = cudaGetLastError();

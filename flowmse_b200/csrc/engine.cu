@@ -41,6 +41,8 @@ constexpr int kNumResBlocks = 2;
 constexpr int kImage = 256;
 constexpr int kAttnRes = 16;
 constexpr int kTemb = 512;
+constexpr int kStatSlotDoubles = 64 * 2;   // per batch element
+constexpr int kMaxStatSlots = 160;
 
 struct ModSpec {
   enum Kind { Fourier, Linear, Conv3, RB, Attn, Combine, GN } kind;
@@ -114,7 +116,7 @@ struct AttnW {
 struct CombW { int c = 0; float *w = nullptr, *b = nullptr; };
 struct HeadW { int c = 0; float *gn_g = nullptr, *gn_b = nullptr, *bias = nullptr; ConvW conv; };
 
-struct Act { float* p = nullptr; int C = 0, H = 0, W = 0; };
+struct Act { float* p = nullptr; int C = 0, H = 0, W = 0; double* qs = nullptr; };   // qs: quad statistics [B][C/4][2]
 
 // kind: 0 misc, 1 gn_stats, 2 gn_prep, 3 conv_gemm, 4 attention, 5 small 4-channel / input kernels, 6 time embedding
 struct Op { std::function<int(cudaStream_t)> fn; int nk; int kind; double flops; int info[4]; };
@@ -347,14 +349,16 @@ struct Builder {
     const double K = static_cast<double>(a.ntaps) * a.Cin + (a.X ? a.Cin2 : 0);
     return 2.0 * a.B * a.H * a.W * a.Cout * K;
   }
+  // one slot = quad statistics of a tensor with up to 256 channels: [B][64][2] doubles
   double* stat_slot() {
-    double* p = plan->stats ? plan->stats + static_cast<size_t>(stat_slots) * B * kGroups * 2 : nullptr;
+    double* p = plan->stats ? plan->stats + static_cast<size_t>(stat_slots) * B * kStatSlotDoubles : nullptr;
     ++stat_slots;
     return p;
   }
   Act new_act(int C, int H, int W) {
     Act a; a.C = C; a.H = H; a.W = W;
     a.p = ar.alloc<float>(static_cast<size_t>(B) * H * W * C);
+    a.qs = stat_slot();
     return a;
   }
 
@@ -365,15 +369,12 @@ struct Builder {
     const int H = in1.H, W = in1.W;
     const int Ho = r.down ? H / 2 : (r.up ? H * 2 : H), Wo = r.down ? W / 2 : (r.up ? W * 2 : W);
     Act out = new_act(r.cout, Ho, Wo);
-    double* st0 = stat_slot();
-    double* st1 = stat_slot();
-    double* gp = plan->gn_partials; unsigned* gc = plan->gn_counters;
-    const int Bc = B;
+    double* st1 = stat_slot();                    // statistics of the Conv_0 output, filled by its epilogue
     const float* s1 = in1.p; const int C1 = in1.C;
     const float* s2 = in2 ? in2->p : nullptr; const int C2 = in2 ? in2->C : 0;
-    push(1, [=](cudaStream_t s) { launch_gn_stats(s1, C1, s2, C2, Bc, H * W, st0, gp, gc, s); return 0; }, 1);
     PrepArgs pa{};
-    pa.src1 = s1; pa.C1 = C1; pa.src2 = s2; pa.C2 = C2; pa.stats = st0; pa.gamma = r.gn0_g; pa.beta = r.gn0_b;
+    pa.src1 = s1; pa.C1 = C1; pa.src2 = s2; pa.C2 = C2; pa.qs1 = in1.qs; pa.qs2 = in2 ? in2->qs : nullptr;
+    pa.gamma = r.gn0_g; pa.beta = r.gn0_b;
     pa.B = B; pa.H = H; pa.W = W; pa.mode = r.down ? kPrepDown : (r.up ? kPrepUp : kPrepPlain); pa.silu = 1;
     pa.outA = scrA; pa.outX = r.has_sc ? scrX : nullptr;
     push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; }, 2);
@@ -382,12 +383,11 @@ struct Builder {
     c0.wscale_inv = r.conv0.wscale_inv; c0.bias = bias_table + r.dense_off; c0.bias_bstride = ctx->dense_rows;
     c0.residual = nullptr; c0.div_sqrt2 = 0; c0.out = scrH1; c0.Cout = r.cout; c0.ldc = r.cout;
     c0.B = B; c0.H = Ho; c0.W = Wo;
-    c0.splitk_scratch = splitk; c0.splitk_scratch_elems = kSplitKScratchElems;
+    c0.splitk_scratch = splitk; c0.splitk_scratch_elems = kSplitKScratchElems; c0.qstats = st1;
     { flowse_ctx* cx = ctx; push(2, [=](cudaStream_t s) { return run_conv(cx, c0, s); }, 3, conv_flops(c0), c0.H, c0.W, c0.ntaps * c0.Cin + (c0.X ? c0.Cin2 : 0), c0.Cout); }
     float* h1 = scrH1; const int Co = r.cout;
-    push(1, [=](cudaStream_t s) { launch_gn_stats(h1, Co, nullptr, 0, Bc, Ho * Wo, st1, gp, gc, s); return 0; }, 1);
     PrepArgs pb{};
-    pb.src1 = h1; pb.C1 = Co; pb.src2 = nullptr; pb.C2 = 0; pb.stats = st1; pb.gamma = r.gn1_g; pb.beta = r.gn1_b;
+    pb.src1 = h1; pb.C1 = Co; pb.src2 = nullptr; pb.C2 = 0; pb.qs1 = st1; pb.gamma = r.gn1_g; pb.beta = r.gn1_b;
     pb.B = B; pb.H = Ho; pb.W = Wo; pb.mode = kPrepPlain; pb.silu = 1; pb.outA = scrA;
     push(1, [=](cudaStream_t s) { launch_gn_prep(pb, s); return 0; }, 2);
     ConvGemmArgs c1{};
@@ -395,7 +395,7 @@ struct Builder {
     c1.Wp = r.conv1.wp; c1.Npad = r.conv1.Npad; c1.wscale_inv = r.conv1.wscale_inv; c1.bias = r.bias1;
     c1.bias_bstride = 0; c1.residual = r.has_sc ? nullptr : s1; c1.div_sqrt2 = 1; c1.out = out.p; c1.Cout = Co;
     c1.ldc = Co; c1.B = B; c1.H = Ho; c1.W = Wo;
-    c1.splitk_scratch = splitk; c1.splitk_scratch_elems = kSplitKScratchElems;
+    c1.splitk_scratch = splitk; c1.splitk_scratch_elems = kSplitKScratchElems; c1.qstats = out.qs;
     { flowse_ctx* cx = ctx; push(2, [=](cudaStream_t s) { return run_conv(cx, c1, s); }, 3, conv_flops(c1), c1.H, c1.W, c1.ntaps * c1.Cin + (c1.X ? c1.Cin2 : 0), c1.Cout); }
     plan->taps[mi] = out;
     return out;
@@ -405,12 +405,10 @@ struct Builder {
     const AttnW& a = ctx->attns.at(mi);
     const int C = a.c, H = in.H, W = in.W, L = H * W, Bc = B;
     Act out = new_act(C, H, W);
-    double* st = stat_slot();
     double* gp = plan->gn_partials; unsigned* gc = plan->gn_counters;
     const float* x = in.p;
-    push(1, [=](cudaStream_t s) { launch_gn_stats(x, C, nullptr, 0, Bc, L, st, gp, gc, s); return 0; }, 1);
     PrepArgs pa{};
-    pa.src1 = x; pa.C1 = C; pa.stats = st; pa.gamma = a.gn_g; pa.beta = a.gn_b; pa.B = B; pa.H = H; pa.W = W;
+    pa.src1 = x; pa.C1 = C; pa.qs1 = in.qs; pa.gamma = a.gn_g; pa.beta = a.gn_b; pa.B = B; pa.H = H; pa.W = W;
     pa.mode = kPrepPlain; pa.silu = 0; pa.outF = scrF;
     push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; }, 2);
     float *hn = scrF, *qkv = scrQKV, *S = scrS, *O = scrO, *o = out.p;
@@ -436,6 +434,7 @@ struct Builder {
       g.M = Bc * L; g.N = C; g.K = C; g.batch = 1; g.alpha = 1.f; g.bias = a.b3; g.residual = x; g.ldr = C;
       g.div_sqrt2 = 1;
       launch_sgemm(g, s); return 0; }, 4);
+    { double* oq = out.qs; push(1, [=](cudaStream_t s) { launch_quad_stats(o, C, Bc, L, oq, gp, gc, s); return 0; }, 1); }
     plan->taps[mi] = out;
     return out;
   }
@@ -462,16 +461,18 @@ struct Builder {
     scrO = ar.alloc<float>(static_cast<size_t>(B) * La * 256);
     scrHead = ar.alloc<float>(top * 4);
     splitk = ar.alloc<float>(kSplitKScratchElems);
-    plan->stats_bytes = static_cast<size_t>(128) * B * kGroups * 2 * sizeof(double);
+    plan->stats_bytes = static_cast<size_t>(kMaxStatSlots) * B * kStatSlotDoubles * sizeof(double);
     plan->stats = ar.alloc<double>(plan->stats_bytes / sizeof(double));
-
-    plan->gn_partials = ar.alloc<double>(static_cast<size_t>(B) * gn_stats_max_blocks() * kGroups * 2);
+    plan->gn_partials = ar.alloc<double>(static_cast<size_t>(B) * gn_stats_max_blocks() * 256);
     plan->gn_counters = ar.alloc<unsigned>(B);      // arena is zero-initialised; the kernel restores zero
 
     // ---- the walk (ncsnpp.py:247-404) ----
     {
       TembWeights tw = ctx->temb; float* td = plan->t_dev; float* ta = temb_act; float* bt = bias_table; const int Bc = B;
       push(2, [=](cudaStream_t s) { launch_temb(tw, td, Bc, ta, bt, s); return 0; }, 6);
+      // producers accumulate quad statistics with atomics: clear all slots once per evaluation
+      double* st = plan->stats; const size_t sb = plan->stats_bytes;
+      push(0, [=](cudaStream_t s) { return cudaMemsetAsync(st, 0, sb, s) == cudaSuccess ? 0 : 1; }, 0);
     }
     std::vector<float4*> pin(kNumLevels);
     for (int l = 0; l < kNumLevels; ++l) pin[l] = ar.alloc<float4>(static_cast<size_t>(B) * (H0 >> l) * (W0 >> l));
@@ -479,8 +480,8 @@ struct Builder {
     Act h0 = new_act(NF, H0, W0);
     {
       const float2 *px = plan->x, *py = plan->y; const float *w = ctx->conv_in_w, *bb = ctx->conv_in_b;
-      float* o = h0.p; float4* p0 = pin[0]; const int Bc = B;
-      push(1, [=](cudaStream_t s) { launch_conv_in(px, py, w, bb, o, p0, Bc, H0, W0, s); return 0; }, 5);
+      float* o = h0.p; float4* p0 = pin[0]; const int Bc = B; double* q0 = h0.qs;
+      push(1, [=](cudaStream_t s) { launch_conv_in(px, py, w, bb, o, p0, q0, Bc, H0, W0, s); return 0; }, 5);
     }
     plan->taps[3] = h0;
     ++m;
@@ -498,9 +499,9 @@ struct Builder {
         Act o = new_act(cw.c, h.H, h.W);
         {
           const float4* src = pin[l]; float4* dst = pin[l + 1]; const int Bc = B, Hh = h.H, Ww = h.W, C = cw.c;
-          const float* hp = h.p; float* op = o.p; const float *w = cw.w, *bb = cw.b;
+          const float* hp = h.p; float* op = o.p; const float *w = cw.w, *bb = cw.b; double* oq = o.qs;
           push(1, [=](cudaStream_t s) { launch_fir_down4(src, dst, Bc, Hh, Ww, s); return 0; }, 5);
-          push(1, [=](cudaStream_t s) { launch_combine(hp, dst, w, bb, op, Bc, Hh, Ww, C, s); return 0; }, 5);
+          push(1, [=](cudaStream_t s) { launch_combine(hp, dst, w, bb, op, oq, Bc, Hh, Ww, C, s); return 0; }, 5);
         }
         plan->taps[m] = o;
         h = o; ++m;
@@ -520,12 +521,9 @@ struct Builder {
       if (h.H == kAttnRes) { h = attention(m, h); ++m; }
       {
         const HeadW& hw = ctx->heads.at(m);
-        double* st = stat_slot();
-        double* gp = plan->gn_partials; unsigned* gc = plan->gn_counters;
         const float* hp = h.p; const int C = h.C, Hh = h.H, Ww = h.W, Bc = B;
-        push(1, [=](cudaStream_t s) { launch_gn_stats(hp, C, nullptr, 0, Bc, Hh * Ww, st, gp, gc, s); return 0; }, 1);
         PrepArgs pa{};
-        pa.src1 = hp; pa.C1 = C; pa.stats = st; pa.gamma = hw.gn_g; pa.beta = hw.gn_b; pa.B = B; pa.H = Hh; pa.W = Ww;
+        pa.src1 = hp; pa.C1 = C; pa.qs1 = h.qs; pa.gamma = hw.gn_g; pa.beta = hw.gn_b; pa.B = B; pa.H = Hh; pa.W = Ww;
         pa.mode = kPrepPlain; pa.silu = 1; pa.outA = scrA;
         push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; }, 2);
         ConvGemmArgs c{};
@@ -544,7 +542,7 @@ struct Builder {
       if (l != 0) { h = resblock(m, h, nullptr); ++m; }
     }
     if (!hs.empty() || m != static_cast<int>(mods.size())) { ctx->err = "internal: module walk mismatch"; return 3; }
-    if (stat_slots > 128) { ctx->err = "internal: too many GroupNorm stat slots"; return 3; }
+    if (stat_slots > kMaxStatSlots) { ctx->err = "internal: too many GroupNorm stat slots"; return 3; }
     plan->pyr_out = pyr_prev;
     return 0;
   }
@@ -862,8 +860,8 @@ int flowse_debug_tap(flowse_ctx* ctx, int module_idx, const float** ptr, int* C,
 
 static int ensure_op_stats(flowse_ctx* ctx) {
   if (ctx->op_stats) return 0;
-  CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_stats), 64 * kGroups * 2 * sizeof(double)));
-  CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_partials), static_cast<size_t>(64) * gn_stats_max_blocks() * kGroups * 2 * sizeof(double)));
+  CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_stats), 2 * 64 * kStatSlotDoubles * sizeof(double)));   // two sources
+  CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_partials), static_cast<size_t>(64) * gn_stats_max_blocks() * 256 * sizeof(double)));
   CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_counters), 64 * sizeof(unsigned)));
   CK(cudaMemset(ctx->op_counters, 0, 64 * sizeof(unsigned)));
   return 0;
@@ -897,9 +895,11 @@ int flowse_op_gn_prep(flowse_ctx* ctx, const float* src1, int C1, const float* s
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (B > 64) { ctx->err = "gn_prep op: B <= 64"; return 2; }
   if (int rc = ensure_op_stats(ctx)) return rc;
-  launch_gn_stats(src1, C1, src2, C2, B, H * W, ctx->op_stats, ctx->op_partials, ctx->op_counters, s);
+  double* qs2 = ctx->op_stats + static_cast<size_t>(64) * kStatSlotDoubles;
+  launch_quad_stats(src1, C1, B, H * W, ctx->op_stats, ctx->op_partials, ctx->op_counters, s);
+  if (src2) launch_quad_stats(src2, C2, B, H * W, qs2, ctx->op_partials, ctx->op_counters, s);
   PrepArgs pa{};
-  pa.src1 = src1; pa.C1 = C1; pa.src2 = src2; pa.C2 = C2; pa.stats = ctx->op_stats; pa.gamma = gamma; pa.beta = beta;
+  pa.src1 = src1; pa.C1 = C1; pa.src2 = src2; pa.C2 = C2; pa.qs1 = ctx->op_stats; pa.qs2 = qs2; pa.gamma = gamma; pa.beta = beta;
   pa.B = B; pa.H = H; pa.W = W; pa.mode = mode; pa.silu = silu;
   pa.outA = static_cast<__half*>(outA); pa.outX = static_cast<__half*>(outX); pa.outF = outF; pa.outXF = outXF;
   launch_gn_prep(pa, s);
@@ -949,9 +949,9 @@ int flowse_op_attention(flowse_ctx* ctx, int module_idx, const float* x, float* 
   float* qkv = hn + static_cast<size_t>(B) * L * C;
   float* O = qkv + static_cast<size_t>(B) * L * 3 * C;
   float* S = O + static_cast<size_t>(B) * L * C;
-  launch_gn_stats(x, C, nullptr, 0, B, L, ctx->op_stats, ctx->op_partials, ctx->op_counters, s);
+  launch_quad_stats(x, C, B, L, ctx->op_stats, ctx->op_partials, ctx->op_counters, s);
   PrepArgs pa{};
-  pa.src1 = x; pa.C1 = C; pa.stats = ctx->op_stats; pa.gamma = a.gn_g; pa.beta = a.gn_b; pa.B = B; pa.H = H; pa.W = W;
+  pa.src1 = x; pa.C1 = C; pa.qs1 = ctx->op_stats; pa.gamma = a.gn_g; pa.beta = a.gn_b; pa.B = B; pa.H = H; pa.W = W;
   pa.mode = kPrepPlain; pa.silu = 0; pa.outF = hn;
   launch_gn_prep(pa, s);
   SgemmArgs g{};

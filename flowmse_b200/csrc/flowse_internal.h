@@ -46,12 +46,13 @@ void launch_temb(const TembWeights& w, const float* t, int B, float* temb_act, f
 
 // conv3x3 4->128 on (x.re, x.im, y.re, y.im) (ncsnpp.py:253-254,285); also writes the 4-plane input pyramid.
 void launch_conv_in(const float2* x, const float2* y, const float* w /*[128][4][3][3]*/, const float* bias,
-                    float* out /*[B,H,W,128]*/, float4* pyr /*[B,H,W,4]*/, int B, int H, int W, cudaStream_t s);
+                    float* out /*[B,H,W,128]*/, float4* pyr /*[B,H,W,4]*/, double* qstats /*[B][32][2] zeroed*/,
+                    int B, int H, int W, cudaStream_t s);
 // 4-channel FIR downsample x2 of the input pyramid (ncsnpp.py:310): [B,2H,2W,4] -> [B,H,W,4]
 void launch_fir_down4(const float4* in, float4* out, int B, int H, int W, cudaStream_t s);
 // Combine(method='sum') (layerspp.py:52-57): out = h + conv1x1(4->C)(pyr) + b
 void launch_combine(const float* h, const float4* pyr, const float* w /*[C][4]*/, const float* b, float* out,
-                    int B, int H, int W, int C, cudaStream_t s);
+                    double* qstats /*[B][C/4][2] zeroed*/, int B, int H, int W, int C, cudaStream_t s);
 // pyramid = FIR-up(prev) + head (ncsnpp.py:357-363). prev may be null (deepest level). head ld = 4.
 void launch_pyr_accum(const float4* prev /*[B,H/2,W/2,4]*/, const float4* head, float4* out, int B, int H, int W,
                       cudaStream_t s);
@@ -67,18 +68,19 @@ void launch_softmax_rows(float* s, int rows, int cols, cudaStream_t st);
 // ---------------------------------------------------------------------------------------------
 // GroupNorm statistics + operand preparation (kernels_gn.cu)
 // ---------------------------------------------------------------------------------------------
-// stats[b][g] = {mean, 1/sqrt(var+eps)} (double) over the channel-concatenation of src1 (C1 ch) and src2 (C2 ch, may be
-// null).  partials: scratch of B * gn_stats_max_blocks() * 64 doubles; counters: B unsigned, zero before first use
-// (the kernel leaves them zero).  Deterministic (no floating-point atomics).
+// Quad statistics qs[b][C/4] = {sum, sum of squares} (double2) of an NHWC fp32 tensor [B][npix][C]; GroupNorm consumers
+// assemble their (possibly concat-straddling) groups from them.  Fused producers accumulate with fp64 atomics into a
+// zeroed buffer; this standalone kernel overwrites.  partials: scratch of B * gn_stats_max_blocks() * 256 doubles;
+// counters: B unsigned, zero before first use (left zero).
 int gn_stats_max_blocks();
-void launch_gn_stats(const float* src1, int C1, const float* src2, int C2, int B, int npix, double* stats,
-                     double* partials, unsigned* counters, cudaStream_t s);
+void launch_quad_stats(const float* src, int C, int B, int npix, double* qs, double* partials, unsigned* counters,
+                       cudaStream_t s);
 
 enum PrepMode { kPrepPlain = 0, kPrepDown = 1, kPrepUp = 2 };
 struct PrepArgs {
   const float* src1; int C1;
   const float* src2; int C2;      // virtual concat [src1, src2] on the channel axis
-  const double* stats;            // [B][32][2] = {mean, rstd} from launch_gn_stats
+  const double* qs1; const double* qs2;   // quad statistics of src1 / src2 ([B][C/4][2] doubles)
   const float* gamma; const float* beta;
   int B, H, W;                    // INPUT resolution
   int mode;                       // PrepMode: output resolution is H/2 (down), 2H (up)
@@ -110,6 +112,7 @@ struct ConvGemmArgs {
   int Cout;             // valid output channels (<= Npad)
   int ldc;
   int B, H, W;
+  double* qstats;               // optional: accumulate quad statistics of the OUTPUT ([B][Cout/4][2], zeroed)
   float* splitk_scratch;        // optional fp32 scratch enabling split-K for low-resolution layers (may be null)
   size_t splitk_scratch_elems;
 };

@@ -34,46 +34,43 @@ __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
 __device__ __forceinline__ uint4 pack8(const uint2 a, const uint2 b) { return make_uint4(a.x, a.y, b.x, b.y); }
 
 // ---------------------------------------------------------------------------------------------
-// statistics: per (batch, group) mean and 1/sqrt(var + eps).
-// Deterministic: block partials (fixed-order shared-memory reduce) go to a scratch array; the LAST block to finish
-// (ticket counter) sums them in block order in double and writes {mean, rstd}.  No float atomics, no memset.
+// "Quad statistics": per (batch, 4-channel quad) sum and sum of squares in double.  Any GroupNorm grouping whose group
+// size is a multiple of 4 channels - including groups that straddle a channel concatenation - is assembled from them
+// in the consumer's prologue.  Producers (conv epilogue, split-K reduce, conv_in, combine) accumulate these with
+// fp64 atomics while they still hold the values, so the tensor is not re-read.  This standalone kernel serves the
+// few tensors without a fusing producer (attention outputs, op-level API): block partials + last-block finalize,
+// fixed summation order, overwrites its output (no zeroing needed).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const float* __restrict__ s1, int C1, const float* __restrict__ s2, int C2, int npix, int chunk,
-                double* __restrict__ stats, double* __restrict__ partials, unsigned* __restrict__ counters) {
-  const int C = C1 + C2;
-  const int cvec = C >> 2;                 // float4 per pixel
+quad_stats_kernel(const float* __restrict__ src, int C, int npix, int chunk, double* __restrict__ qs,
+                  double* __restrict__ partials, unsigned* __restrict__ counters) {
+  const int cvec = C >> 2;                 // quads per pixel
   const int ppi = blockDim.x / cvec;       // pixels per iteration
   const int b = blockIdx.y;
   const int nblk = gridDim.x;
   __shared__ float ts[256], tq[256];
-  __shared__ double fs[8][kGroups], fq[8][kGroups];
   __shared__ bool is_last;
   const int v = threadIdx.x % cvec;
   const int pp = threadIdx.x / cvec;
   float s = 0.f, q = 0.f;
   if (pp < ppi) {
-    const int c = v << 2;
-    const float* src;
-    int ld, cc;
-    if (c < C1) { src = s1; ld = C1; cc = c; } else { src = s2; ld = C2; cc = c - C1; }
     const int p0 = blockIdx.x * chunk;
     const int p1 = min(npix, p0 + chunk);
-    const float* base = src + static_cast<size_t>(b) * npix * ld + cc;
+    const float* base = src + static_cast<size_t>(b) * npix * C + (v << 2);
     int p = p0 + pp;
     float s1a = 0.f, q1a = 0.f, s2a = 0.f, q2a = 0.f, s3a = 0.f, q3a = 0.f;
     for (; p + 3 * ppi < p1; p += 4 * ppi) {        // 4 independent 16-byte loads in flight per thread
-      const float4 x0 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * ld));
-      const float4 x1 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + ppi) * ld));
-      const float4 x2 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + 2 * ppi) * ld));
-      const float4 x3 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + 3 * ppi) * ld));
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * C));
+      const float4 x1 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + ppi) * C));
+      const float4 x2 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + 2 * ppi) * C));
+      const float4 x3 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + 3 * ppi) * C));
       s += (x0.x + x0.y) + (x0.z + x0.w);   q += (x0.x * x0.x + x0.y * x0.y) + (x0.z * x0.z + x0.w * x0.w);
       s1a += (x1.x + x1.y) + (x1.z + x1.w); q1a += (x1.x * x1.x + x1.y * x1.y) + (x1.z * x1.z + x1.w * x1.w);
       s2a += (x2.x + x2.y) + (x2.z + x2.w); q2a += (x2.x * x2.x + x2.y * x2.y) + (x2.z * x2.z + x2.w * x2.w);
       s3a += (x3.x + x3.y) + (x3.z + x3.w); q3a += (x3.x * x3.x + x3.y * x3.y) + (x3.z * x3.z + x3.w * x3.w);
     }
     for (; p < p1; p += ppi) {
-      const float4 x = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * ld));
+      const float4 x = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * C));
       s += (x.x + x.y) + (x.z + x.w);
       q += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
     }
@@ -82,17 +79,13 @@ gn_stats_kernel(const float* __restrict__ s1, int C1, const float* __restrict__ 
   }
   ts[threadIdx.x] = s; tq[threadIdx.x] = q;
   __syncthreads();
-  const int vpg = cvec / kGroups;          // float4 lanes per group (1, 2, 3 or 4)
-  if (threadIdx.x < kGroups) {
-    const int g = threadIdx.x;
+  if (threadIdx.x < cvec) {                // one thread per quad sums the ppi pixel rows in fixed order
     double as = 0.0, aq = 0.0;
-    for (int r = 0; r < ppi; ++r)
-      for (int j = 0; j < vpg; ++j) {
-        const int t = r * cvec + g * vpg + j;
-        as += static_cast<double>(ts[t]); aq += static_cast<double>(tq[t]);
-      }
-    double2* dst = reinterpret_cast<double2*>(partials) + (static_cast<size_t>(b) * nblk + blockIdx.x) * kGroups + g;
-    *dst = make_double2(as, aq);
+    for (int r = 0; r < ppi; ++r) {
+      as += static_cast<double>(ts[r * cvec + threadIdx.x]); aq += static_cast<double>(tq[r * cvec + threadIdx.x]);
+    }
+    reinterpret_cast<double2*>(partials)[(static_cast<size_t>(b) * nblk + blockIdx.x) * cvec + threadIdx.x] =
+        make_double2(as, aq);
   }
   __threadfence();
   __syncthreads();
@@ -100,39 +93,21 @@ gn_stats_kernel(const float* __restrict__ s1, int C1, const float* __restrict__ 
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  {
-    // warp w sums blocks w, w+8, ... (lane = group): coalesced 512-byte rows, 4 loads in flight
-    const int g = threadIdx.x & 31, part = threadIdx.x >> 5;
-    const double2* src = reinterpret_cast<const double2*>(partials) + static_cast<size_t>(b) * nblk * kGroups + g;
-    double as = 0.0, aq = 0.0;
-    int k = part;
-    for (; k + 24 < nblk; k += 32) {
-      const double2 v0 = __ldcg(src + static_cast<size_t>(k) * kGroups);
-      const double2 v1 = __ldcg(src + static_cast<size_t>(k + 8) * kGroups);
-      const double2 v2 = __ldcg(src + static_cast<size_t>(k + 16) * kGroups);
-      const double2 v3 = __ldcg(src + static_cast<size_t>(k + 24) * kGroups);
-      as += v0.x; aq += v0.y; as += v1.x; aq += v1.y; as += v2.x; aq += v2.y; as += v3.x; aq += v3.y;
+  if (threadIdx.x < cvec) {
+    const double2* src2 = reinterpret_cast<const double2*>(partials) + static_cast<size_t>(b) * nblk * cvec + threadIdx.x;
+    double as = 0.0, aq = 0.0, bs = 0.0, bq = 0.0;
+    int k = 0;
+    for (; k + 3 < nblk; k += 4) {        // 4 coalesced loads in flight, fixed order
+      const double2 v0 = __ldcg(src2 + static_cast<size_t>(k) * cvec);
+      const double2 v1 = __ldcg(src2 + static_cast<size_t>(k + 1) * cvec);
+      const double2 v2 = __ldcg(src2 + static_cast<size_t>(k + 2) * cvec);
+      const double2 v3 = __ldcg(src2 + static_cast<size_t>(k + 3) * cvec);
+      as += v0.x; aq += v0.y; bs += v1.x; bq += v1.y; as += v2.x; aq += v2.y; bs += v3.x; bq += v3.y;
     }
-    for (; k < nblk; k += 8) {
-      const double2 v0 = __ldcg(src + static_cast<size_t>(k) * kGroups);
-      as += v0.x; aq += v0.y;
-    }
-    fs[part][g] = as; fq[part][g] = aq;
+    for (; k < nblk; ++k) { const double2 v0 = __ldcg(src2 + static_cast<size_t>(k) * cvec); as += v0.x; aq += v0.y; }
+    reinterpret_cast<double2*>(qs)[static_cast<size_t>(b) * cvec + threadIdx.x] = make_double2(as + bs, aq + bq);
   }
-  __syncthreads();
-  if (threadIdx.x < kGroups) {
-    const int g = threadIdx.x;
-    double as = 0.0, aq = 0.0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { as += fs[k][g]; aq += fq[k][g]; }
-    const double n = static_cast<double>(npix) * (C / kGroups);
-    const double mean = as / n;
-    double var = aq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stats[(static_cast<size_t>(b) * kGroups + g) * 2 + 0] = mean;
-    stats[(static_cast<size_t>(b) * kGroups + g) * 2 + 1] = 1.0 / sqrt(var + static_cast<double>(kGnEps));
-  }
-  if (threadIdx.x == 0) counters[b] = 0u;    // ready for the next GroupNorm on this stream
+  if (threadIdx.x == 0) counters[b] = 0u;    // ready for the next call on this stream
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -141,7 +116,7 @@ gn_stats_kernel(const float* __restrict__ s1, int C1, const float* __restrict__ 
 struct PrepK {
   const float* s1; int C1;
   const float* s2; int C2;
-  const double* stats;
+  const double* qs1; const double* qs2;     // quad statistics of s1 / s2: [B][C/4][2]
   const float* gamma; const float* beta;
   int H, W, Ho, Wo, mode, silu, B;
   __half* outA; __half* outX; float* outF; float* outXF;
@@ -172,10 +147,26 @@ __device__ __forceinline__ void scale_shift(const PrepK& k, const float* s_mean,
   sh.z = fmaf(-mean, sc.z, be.z); sh.w = fmaf(-mean, sc.w, be.w);
 }
 
+// Group mean / rstd from the quad statistics of the (virtually concatenated) sources.
 __device__ __forceinline__ void load_stats(const PrepK& k, int b, float* s_mean, float* s_rstd) {
   if (threadIdx.x < kGroups) {
-    s_mean[threadIdx.x] = static_cast<float>(k.stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 0]);
-    s_rstd[threadIdx.x] = static_cast<float>(k.stats[(static_cast<size_t>(b) * kGroups + threadIdx.x) * 2 + 1]);
+    const int C = k.C1 + k.C2;
+    const int qpg = (C / kGroups) >> 2;            // quads per group
+    const int q1 = k.C1 >> 2;
+    double su = 0.0, sq = 0.0;
+    for (int j = 0; j < qpg; ++j) {
+      const int qd = threadIdx.x * qpg + j;
+      const double2 v = (qd < q1)
+          ? reinterpret_cast<const double2*>(k.qs1)[static_cast<size_t>(b) * q1 + qd]
+          : reinterpret_cast<const double2*>(k.qs2)[static_cast<size_t>(b) * (k.C2 >> 2) + (qd - q1)];
+      su += v.x; sq += v.y;
+    }
+    const double n = static_cast<double>(k.H) * k.W * (C / kGroups);
+    const double mean = su / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
   }
   __syncthreads();
 }
@@ -323,9 +314,8 @@ gn_prep_resample_kernel(const PrepK k) {
 
 int gn_stats_max_blocks() { return 296; }
 
-void launch_gn_stats(const float* src1, int C1, const float* src2, int C2, int B, int npix, double* stats,
-                     double* partials, unsigned* counters, cudaStream_t s) {
-  const int C = C1 + (src2 ? C2 : 0);
+void launch_quad_stats(const float* src, int C, int B, int npix, double* qs, double* partials, unsigned* counters,
+                       cudaStream_t s) {
   const int cvec = C / 4;
   const int ppi = 256 / cvec;
   int target_blocks = std::max(1, std::min(gn_stats_max_blocks(), 592 / B));
@@ -333,14 +323,14 @@ void launch_gn_stats(const float* src1, int C1, const float* src2, int C2, int B
   chunk = ((chunk + ppi - 1) / ppi) * ppi;
   if (chunk < ppi * 4) chunk = ppi * 4;
   dim3 grid((npix + chunk - 1) / chunk, B);
-  gn_stats_kernel<<<grid, 256, 0, s>>>(src1, C1, src2, src2 ? C2 : 0, npix, chunk, stats, partials, counters);
+  quad_stats_kernel<<<grid, 256, 0, s>>>(src, C, npix, chunk, qs, partials, counters);
   ++launch_counter();
 }
 
 void launch_gn_prep(const PrepArgs& a, cudaStream_t s) {
   PrepK k;
   k.s1 = a.src1; k.C1 = a.C1; k.s2 = a.src2; k.C2 = a.src2 ? a.C2 : 0;
-  k.stats = a.stats; k.gamma = a.gamma; k.beta = a.beta;
+  k.qs1 = a.qs1; k.qs2 = a.qs2; k.gamma = a.gamma; k.beta = a.beta;
   k.H = a.H; k.W = a.W; k.mode = a.mode; k.silu = a.silu; k.B = a.B;
   k.Ho = a.mode == kPrepDown ? a.H / 2 : (a.mode == kPrepUp ? a.H * 2 : a.H);
   k.Wo = a.mode == kPrepDown ? a.W / 2 : (a.mode == kPrepUp ? a.W * 2 : a.W);

@@ -153,7 +153,8 @@ temb_dense_kernel(const float* __restrict__ dw, const float* __restrict__ db, co
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const float* __restrict__ wgt,
-               const float* __restrict__ bias, float* __restrict__ out, float4* __restrict__ pyr, int H, int W) {
+               const float* __restrict__ bias, float* __restrict__ out, float4* __restrict__ pyr,
+               double* __restrict__ qstats, int H, int W) {
   __shared__ float4 s_in[6][34];          // 4 channels per pixel, halo 1
   __shared__ float4 s_w[9][4][32];        // [tap][ci][lane] -> 4 consecutive output channels
   const int b = blockIdx.z;
@@ -206,6 +207,7 @@ conv_in_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const
     }
   }
   const int h = h0 + row;
+  float qs_s = 0.f, qs_q = 0.f;
   if (h < H) {
 #pragma unroll
     for (int p = 0; p < 16; ++p) {
@@ -213,7 +215,22 @@ conv_in_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const
       if (w < W) {
         const size_t pix = (static_cast<size_t>(b) * H + h) * W + w;
         reinterpret_cast<float4*>(out + pix * 128)[lane] = acc[p];
+        qs_s += (acc[p].x + acc[p].y) + (acc[p].z + acc[p].w);
+        qs_q += (acc[p].x * acc[p].x + acc[p].y * acc[p].y) + (acc[p].z * acc[p].z + acc[p].w * acc[p].w);
       }
+    }
+  }
+  if (qstats) {            // lane == channel quad; fold the 8 warps through shared memory, one atomic pair per quad
+    __shared__ float rs[8][32], rq[8][32];
+    rs[g][lane] = qs_s; rq[g][lane] = qs_q;
+    __syncthreads();
+    if (g == 0) {
+      float as = 0.f, aq = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { as += rs[k][lane]; aq += rq[k][lane]; }
+      double* dst = qstats + (static_cast<size_t>(b) * 32 + lane) * 2;
+      atomicAdd(dst, static_cast<double>(as));
+      atomicAdd(dst + 1, static_cast<double>(aq));
     }
   }
 }
@@ -250,30 +267,48 @@ fir_down4_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B,
   out[i] = acc;
 }
 
-// out = h + conv1x1(4->C)(pyr) + b                  (Combine 'sum', layerspp.py:52-57)
+// out = h + conv1x1(4->C)(pyr) + b                  (Combine 'sum', layerspp.py:52-57); grid = (blocks, B).
+// A thread owns one channel quad for all its pixels (weights in registers) and accumulates the output's quad stats.
 __global__ void __launch_bounds__(256)
 combine_kernel(const float* __restrict__ h, const float4* __restrict__ pyr, const float* __restrict__ w,
-               const float* __restrict__ bias, float* __restrict__ out, size_t npix, int C) {
+               const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ qstats, int npix, int C) {
   const int cvec = C >> 2;
-  const size_t total = npix * cvec;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int v = i % cvec;
-    const size_t pix = i / cvec;
-    const int c = v << 2;
-    const float4 p = __ldg(pyr + pix);
-    const float4 hv = __ldg(reinterpret_cast<const float4*>(h + pix * C + c));
+  const int ppi = blockDim.x / cvec;
+  const int b = blockIdx.y;
+  const int v = threadIdx.x % cvec, pp = threadIdx.x / cvec;
+  const int c = v << 2;
+  __shared__ float ss[256], sq[256];
+  float ls = 0.f, lq = 0.f;
+  if (pp < ppi) {
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (c + 0) * 4));
     const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (c + 1) * 4));
     const float4 w2 = __ldg(reinterpret_cast<const float4*>(w + (c + 2) * 4));
     const float4 w3 = __ldg(reinterpret_cast<const float4*>(w + (c + 3) * 4));
-    float4 o;
-    o.x = hv.x + (fmaf(w0.w, p.w, fmaf(w0.z, p.z, fmaf(w0.y, p.y, w0.x * p.x))) + bv.x);
-    o.y = hv.y + (fmaf(w1.w, p.w, fmaf(w1.z, p.z, fmaf(w1.y, p.y, w1.x * p.x))) + bv.y);
-    o.z = hv.z + (fmaf(w2.w, p.w, fmaf(w2.z, p.z, fmaf(w2.y, p.y, w2.x * p.x))) + bv.z);
-    o.w = hv.w + (fmaf(w3.w, p.w, fmaf(w3.z, p.z, fmaf(w3.y, p.y, w3.x * p.x))) + bv.w);
-    *reinterpret_cast<float4*>(out + pix * C + c) = o;
+    for (int p = blockIdx.x * ppi + pp; p < npix; p += gridDim.x * ppi) {
+      const size_t pix = static_cast<size_t>(b) * npix + p;
+      const float4 pv = __ldg(pyr + pix);
+      const float4 hv = __ldg(reinterpret_cast<const float4*>(h + pix * C + c));
+      float4 o;
+      o.x = hv.x + (fmaf(w0.w, pv.w, fmaf(w0.z, pv.z, fmaf(w0.y, pv.y, w0.x * pv.x))) + bv.x);
+      o.y = hv.y + (fmaf(w1.w, pv.w, fmaf(w1.z, pv.z, fmaf(w1.y, pv.y, w1.x * pv.x))) + bv.y);
+      o.z = hv.z + (fmaf(w2.w, pv.w, fmaf(w2.z, pv.z, fmaf(w2.y, pv.y, w2.x * pv.x))) + bv.z);
+      o.w = hv.w + (fmaf(w3.w, pv.w, fmaf(w3.z, pv.z, fmaf(w3.y, pv.y, w3.x * pv.x))) + bv.w);
+      *reinterpret_cast<float4*>(out + pix * C + c) = o;
+      ls += (o.x + o.y) + (o.z + o.w);
+      lq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+    }
+  }
+  if (qstats) {
+    ss[threadIdx.x] = ls; sq[threadIdx.x] = lq;
+    __syncthreads();
+    if (threadIdx.x < cvec) {
+      float as = 0.f, aq = 0.f;
+      for (int r = 0; r < ppi; ++r) { as += ss[r * cvec + threadIdx.x]; aq += sq[r * cvec + threadIdx.x]; }
+      double* dst = qstats + (static_cast<size_t>(b) * cvec + threadIdx.x) * 2;
+      atomicAdd(dst, static_cast<double>(as));
+      atomicAdd(dst + 1, static_cast<double>(aq));
+    }
   }
 }
 
@@ -400,9 +435,9 @@ void launch_temb(const TembWeights& w, const float* t, int B, float* temb_act, f
 }
 
 void launch_conv_in(const float2* x, const float2* y, const float* w, const float* bias, float* out, float4* pyr,
-                    int B, int H, int W, cudaStream_t s) {
+                    double* qstats, int B, int H, int W, cudaStream_t s) {
   dim3 grid((W + 31) / 32, (H + 3) / 4, B);
-  conv_in_kernel<<<grid, 256, 0, s>>>(x, y, w, bias, out, pyr, H, W);
+  conv_in_kernel<<<grid, 256, 0, s>>>(x, y, w, bias, out, pyr, qstats, H, W);
   ++launch_counter();
 }
 
@@ -412,10 +447,15 @@ void launch_fir_down4(const float4* in, float4* out, int B, int H, int W, cudaSt
   ++launch_counter();
 }
 
-void launch_combine(const float* h, const float4* pyr, const float* w, const float* b, float* out, int B, int H,
-                    int W, int C, cudaStream_t s) {
-  const size_t npix = static_cast<size_t>(B) * H * W;
-  combine_kernel<<<grid_for(npix * (C / 4)), 256, 0, s>>>(h, pyr, w, b, out, npix, C);
+void launch_combine(const float* h, const float4* pyr, const float* w, const float* b, float* out, double* qstats,
+                    int B, int H, int W, int C, cudaStream_t s) {
+  const int npix = H * W;
+  const int ppi = 256 / (C / 4);
+  int blocks = (npix + ppi - 1) / ppi;
+  const int cap = std::max(1, (148 * 8) / B);
+  if (blocks > cap) blocks = cap;
+  dim3 grid(blocks, B);
+  combine_kernel<<<grid, 256, 0, s>>>(h, pyr, w, b, out, qstats, npix, C);
   ++launch_counter();
 }
 
