@@ -317,7 +317,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               qs_q += __shfl_xor_sync(0xffffffffu, qs_q, o);
             }
             if (sub_row == 0) {
-              double* dst = p.qstats + (static_cast<size_t>(b) * (p.Cout >> 2) + (n >> 2)) * 2;
+              double* dst = qstat_slot(p.qstats, b, blockIdx.x, p.Cout >> 2) + static_cast<size_t>(n >> 2) * 2;
               atomicAdd(dst, static_cast<double>(qs_s));
               atomicAdd(dst + 1, static_cast<double>(qs_q));
             }
@@ -370,7 +370,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, int S, long long plane, 
     if (threadIdx.x < ldc4) {
       float as = 0.f, aq = 0.f;
       for (int t = threadIdx.x; t < 256; t += ldc4) { as += ss[t]; aq += sq[t]; }
-      double* dst = qstats + (static_cast<size_t>(b) * ldc4 + threadIdx.x) * 2;
+      double* dst = qstat_slot(qstats, b, blockIdx.x, ldc4) + static_cast<size_t>(threadIdx.x) * 2;
       atomicAdd(dst, static_cast<double>(as));
       atomicAdd(dst + 1, static_cast<double>(aq));
     }
@@ -422,7 +422,7 @@ __global__ void conv_gemm_simt_kernel(const __half* __restrict__ A, const __half
   if (p.div_sqrt2) v = __fdiv_rn(v, kSqrt2);
   p.out[pix * p.ldc + n] = v;
   if (p.qstats) {      // debug path: one fp64 atomic pair per element
-    double* dst = p.qstats + (static_cast<size_t>(b) * (p.Cout >> 2) + (n >> 2)) * 2;
+    double* dst = qstat_slot(p.qstats, b, static_cast<int>(pix), p.Cout >> 2) + static_cast<size_t>(n >> 2) * 2;
     atomicAdd(dst, static_cast<double>(v));
     atomicAdd(dst + 1, static_cast<double>(v) * static_cast<double>(v));
   }

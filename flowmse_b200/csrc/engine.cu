@@ -41,7 +41,7 @@ constexpr int kNumResBlocks = 2;
 constexpr int kImage = 256;
 constexpr int kAttnRes = 16;
 constexpr int kTemb = 512;
-constexpr int kStatSlotDoubles = 64 * 2;   // per batch element
+constexpr int kStatSlotDoubles = kStatReplicas * 64 * 2;   // per batch element: up to 256 channels
 constexpr int kMaxStatSlots = 160;
 
 struct ModSpec {
@@ -322,9 +322,16 @@ struct Arena {
   }
 };
 
+// conv_impl: 0 = auto (halo kernel for the high-resolution layers, per-tap kernel otherwise), 1 = SIMT cross-check,
+// 2 = per-tap tcgen05 kernel everywhere, 3 = auto with 3 rotating main accumulators in the halo kernel.
 int run_conv(flowse_ctx* ctx, const ConvGemmArgs& a, cudaStream_t s) {
   std::string e;
-  const int rc = ctx->conv_impl == 1 ? launch_conv_gemm_simt(a, s, &e) : launch_conv_gemm(a, s, &e);
+  int rc;
+  if (ctx->conv_impl == 1) rc = launch_conv_gemm_simt(a, s, &e);
+  else if (ctx->conv_impl != 2 && conv_halo_supported(a) &&
+           static_cast<long long>(a.B) * (a.H / 16) * (a.W / 8) * ((a.Cout + 127) / 128) >= 100)
+    rc = launch_conv_halo(a, ctx->conv_impl == 3 ? 3 : 1, s, &e);
+  else rc = launch_conv_gemm(a, s, &e);
   if (rc) ctx->err = e;
   return rc;
 }
@@ -920,8 +927,11 @@ int flowse_op_conv_gemm(flowse_ctx* ctx, const void* A, int Cin, int ntaps, cons
   if (!ctx->op_splitk) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_splitk), kSplitKScratchElems * sizeof(float)));
   a.splitk_scratch = ctx->op_splitk; a.splitk_scratch_elems = kSplitKScratchElems;
   std::string e;
-  const int rc = impl == 1 ? launch_conv_gemm_simt(a, static_cast<cudaStream_t>(stream), &e)
-                           : launch_conv_gemm(a, static_cast<cudaStream_t>(stream), &e);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if (impl == 1) rc = launch_conv_gemm_simt(a, st, &e);
+  else if (impl == 2 || impl == 3) rc = launch_conv_halo(a, impl == 3 ? 3 : 1, st, &e);   // halo kernel, 1 / 3 main slots
+  else rc = launch_conv_gemm(a, st, &e);
   if (rc) ctx->err = e;
   return rc;
 }

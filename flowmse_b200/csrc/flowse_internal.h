@@ -15,6 +15,16 @@ constexpr int kGroups = 32;          // GroupNorm groups: min(C/4, 32) == 32 for
 constexpr float kGnEps = 1e-6f;
 constexpr float kSqrt2 = 1.41421356237309504880f;   // np.sqrt(2.) rounded to fp32 (layerspp.py:274)
 
+// Quad statistics of one tensor: [B][kStatReplicas][C/4]{sum, sumsq} in fp64.  Producers spread their atomics over the
+// replicas (keyed by tile / block index) so that one address is not hammered by every CTA; consumers add them up.
+constexpr int kStatReplicas = 8;
+__host__ __device__ inline double* qstat_slot(double* base, int b, int replica_key, int quads) {
+  return base + (static_cast<size_t>(b) * kStatReplicas + (replica_key & (kStatReplicas - 1))) * quads * 2;
+}
+__host__ __device__ inline const double* qstat_slot(const double* base, int b, int replica_key, int quads) {
+  return base + (static_cast<size_t>(b) * kStatReplicas + (replica_key & (kStatReplicas - 1))) * quads * 2;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Element-wise / small kernels (kernels_pointwise.cu)
 // ---------------------------------------------------------------------------------------------
@@ -46,13 +56,13 @@ void launch_temb(const TembWeights& w, const float* t, int B, float* temb_act, f
 
 // conv3x3 4->128 on (x.re, x.im, y.re, y.im) (ncsnpp.py:253-254,285); also writes the 4-plane input pyramid.
 void launch_conv_in(const float2* x, const float2* y, const float* w /*[128][4][3][3]*/, const float* bias,
-                    float* out /*[B,H,W,128]*/, float4* pyr /*[B,H,W,4]*/, double* qstats /*[B][32][2] zeroed*/,
+                    float* out /*[B,H,W,128]*/, float4* pyr /*[B,H,W,4]*/, double* qstats /*quad statistics of the output, zeroed*/,
                     int B, int H, int W, cudaStream_t s);
 // 4-channel FIR downsample x2 of the input pyramid (ncsnpp.py:310): [B,2H,2W,4] -> [B,H,W,4]
 void launch_fir_down4(const float4* in, float4* out, int B, int H, int W, cudaStream_t s);
 // Combine(method='sum') (layerspp.py:52-57): out = h + conv1x1(4->C)(pyr) + b
 void launch_combine(const float* h, const float4* pyr, const float* w /*[C][4]*/, const float* b, float* out,
-                    double* qstats /*[B][C/4][2] zeroed*/, int B, int H, int W, int C, cudaStream_t s);
+                    double* qstats /*quad statistics of the output, zeroed*/, int B, int H, int W, int C, cudaStream_t s);
 // pyramid = FIR-up(prev) + head (ncsnpp.py:357-363). prev may be null (deepest level). head ld = 4.
 void launch_pyr_accum(const float4* prev /*[B,H/2,W/2,4]*/, const float4* head, float4* out, int B, int H, int W,
                       cudaStream_t s);
@@ -68,9 +78,9 @@ void launch_softmax_rows(float* s, int rows, int cols, cudaStream_t st);
 // ---------------------------------------------------------------------------------------------
 // GroupNorm statistics + operand preparation (kernels_gn.cu)
 // ---------------------------------------------------------------------------------------------
-// Quad statistics qs[b][C/4] = {sum, sum of squares} (double2) of an NHWC fp32 tensor [B][npix][C]; GroupNorm consumers
-// assemble their (possibly concat-straddling) groups from them.  Fused producers accumulate with fp64 atomics into a
-// zeroed buffer; this standalone kernel overwrites.  partials: scratch of B * gn_stats_max_blocks() * 256 doubles;
+// Quad statistics (layout above) of an NHWC fp32 tensor [B][npix][C]; GroupNorm consumers assemble their (possibly
+// concat-straddling) groups from them.  Fused producers accumulate with fp64 atomics into a zeroed buffer; this
+// standalone kernel overwrites replica 0 (the others must be zero).  partials: scratch of B * gn_stats_max_blocks() * 256 doubles;
 // counters: B unsigned, zero before first use (left zero).
 int gn_stats_max_blocks();
 void launch_quad_stats(const float* src, int C, int B, int npix, double* qs, double* partials, unsigned* counters,
@@ -80,7 +90,7 @@ enum PrepMode { kPrepPlain = 0, kPrepDown = 1, kPrepUp = 2 };
 struct PrepArgs {
   const float* src1; int C1;
   const float* src2; int C2;      // virtual concat [src1, src2] on the channel axis
-  const double* qs1; const double* qs2;   // quad statistics of src1 / src2 ([B][C/4][2] doubles)
+  const double* qs1; const double* qs2;   // quad statistics of src1 / src2
   const float* gamma; const float* beta;
   int B, H, W;                    // INPUT resolution
   int mode;                       // PrepMode: output resolution is H/2 (down), 2H (up)
@@ -112,7 +122,7 @@ struct ConvGemmArgs {
   int Cout;             // valid output channels (<= Npad)
   int ldc;
   int B, H, W;
-  double* qstats;               // optional: accumulate quad statistics of the OUTPUT ([B][Cout/4][2], zeroed)
+  double* qstats;               // optional: accumulate quad statistics of the OUTPUT (zeroed buffer)
   float* splitk_scratch;        // optional fp32 scratch enabling split-K for low-resolution layers (may be null)
   size_t splitk_scratch_elems;
 };
@@ -121,6 +131,10 @@ constexpr size_t kSplitKScratchElems = static_cast<size_t>(148) * 128 * 128;   /
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t s, std::string* err);
 // Slow SIMT evaluation of exactly the same operands (debug / cross-check only; never on the product path).
 int launch_conv_gemm_simt(const ConvGemmArgs& a, cudaStream_t s, std::string* err);
+// Halo variant (conv_halo.cu): persistent, one TMA halo load per 64-channel chunk, 3x3 only, H % 16 == 0, W % 8 == 0.
+// nmain = number of rotating hi*hi accumulator slots (1: double-buffered TMEM, 3: single buffer).
+bool conv_halo_supported(const ConvGemmArgs& a);
+int launch_conv_halo(const ConvGemmArgs& a, int nmain, cudaStream_t s, std::string* err);
 // Host-side packing: fp32 [Cout][Cin][kh][kw] (+ optional 1x1 shortcut [Cout][Cin2]) -> K-major fp16 hi/lo.
 // out_hi/out_lo: [Npad][K]; returns the power-of-two exponent used.
 int pack_conv_weights_host(const float* w_main, int Cout, int Cin, int ntaps, const float* w_sc, int Cin2,

@@ -105,7 +105,7 @@ quad_stats_kernel(const float* __restrict__ src, int C, int npix, int chunk, dou
       as += v0.x; aq += v0.y; bs += v1.x; bq += v1.y; as += v2.x; aq += v2.y; bs += v3.x; bq += v3.y;
     }
     for (; k < nblk; ++k) { const double2 v0 = __ldcg(src2 + static_cast<size_t>(k) * cvec); as += v0.x; aq += v0.y; }
-    reinterpret_cast<double2*>(qs)[static_cast<size_t>(b) * cvec + threadIdx.x] = make_double2(as + bs, aq + bq);
+    reinterpret_cast<double2*>(qstat_slot(qs, b, 0, cvec))[threadIdx.x] = make_double2(as + bs, aq + bq);
   }
   if (threadIdx.x == 0) counters[b] = 0u;    // ready for the next call on this stream
 }
@@ -156,10 +156,13 @@ __device__ __forceinline__ void load_stats(const PrepK& k, int b, float* s_mean,
     double su = 0.0, sq = 0.0;
     for (int j = 0; j < qpg; ++j) {
       const int qd = threadIdx.x * qpg + j;
-      const double2 v = (qd < q1)
-          ? reinterpret_cast<const double2*>(k.qs1)[static_cast<size_t>(b) * q1 + qd]
-          : reinterpret_cast<const double2*>(k.qs2)[static_cast<size_t>(b) * (k.C2 >> 2) + (qd - q1)];
-      su += v.x; sq += v.y;
+#pragma unroll
+      for (int r = 0; r < kStatReplicas; ++r) {       // fixed order over the replicas
+        const double2 v = (qd < q1)
+            ? reinterpret_cast<const double2*>(qstat_slot(k.qs1, b, r, q1))[qd]
+            : reinterpret_cast<const double2*>(qstat_slot(k.qs2, b, r, k.C2 >> 2))[qd - q1];
+        su += v.x; sq += v.y;
+      }
     }
     const double n = static_cast<double>(k.H) * k.W * (C / kGroups);
     const double mean = su / n;

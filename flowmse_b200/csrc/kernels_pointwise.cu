@@ -228,7 +228,7 @@ conv_in_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const
       float as = 0.f, aq = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) { as += rs[k][lane]; aq += rq[k][lane]; }
-      double* dst = qstats + (static_cast<size_t>(b) * 32 + lane) * 2;
+      double* dst = qstat_slot(qstats, b, blockIdx.y * gridDim.x + blockIdx.x, 32) + static_cast<size_t>(lane) * 2;
       atomicAdd(dst, static_cast<double>(as));
       atomicAdd(dst + 1, static_cast<double>(aq));
     }
@@ -305,7 +305,7 @@ combine_kernel(const float* __restrict__ h, const float4* __restrict__ pyr, cons
     if (threadIdx.x < cvec) {
       float as = 0.f, aq = 0.f;
       for (int r = 0; r < ppi; ++r) { as += ss[r * cvec + threadIdx.x]; aq += sq[r * cvec + threadIdx.x]; }
-      double* dst = qstats + (static_cast<size_t>(b) * cvec + threadIdx.x) * 2;
+      double* dst = qstat_slot(qstats, b, blockIdx.x, cvec) + static_cast<size_t>(threadIdx.x) * 2;
       atomicAdd(dst, static_cast<double>(as));
       atomicAdd(dst + 1, static_cast<double>(aq));
     }

@@ -75,7 +75,8 @@ int flowse_euler_step(flowse_ctx* ctx, const void* x, const void* v, float steps
 int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const void* z, const float* timesteps_host, int N, int solver,
                   float sigma, void* x_out, int B, int T, void* stream);
 
-/* Options: "conv_impl" 0 = tcgen05 (default), 1 = SIMT cross-check; "graph" 0/1 = replay each NFE as a CUDA graph. */
+/* Options: "conv_impl" 0 = tcgen05 (default: halo kernel on high-resolution layers, per-tap kernel otherwise),
+ * 1 = SIMT cross-check, 2 = per-tap kernel everywhere, 3 = like 0 with 3 rotating main accumulators in the halo kernel; "graph" 0/1 = replay each NFE as a CUDA graph. */
 int flowse_set_option(flowse_ctx* ctx, const char* key, int value);
 
 /* Number of this library's kernel launches (graph kernel nodes included) since the context was created. */
@@ -106,7 +107,8 @@ int flowse_op_gn_prep(flowse_ctx* ctx, const float* src1, int C1, const float* s
                       const float* beta, int B, int H, int W, int mode, int silu, void* outA, void* outX, float* outF,
                       float* outXF, void* stream);
 
-/* Implicit-GEMM conv (3x3 pad 1 when ntaps == 9, 1x1 when 1) on hi/lo operands; impl 0 = tcgen05, 1 = SIMT. */
+/* Implicit-GEMM conv (3x3 pad 1 when ntaps == 9, 1x1 when 1) on hi/lo operands; impl 0 = per-tap tcgen05 kernel,
+ * 1 = SIMT cross-check, 2 / 3 = halo tcgen05 kernel (3x3, H % 16 == 0, W % 8 == 0) with 1 / 3 main accumulators. */
 int flowse_op_conv_gemm(flowse_ctx* ctx, const void* A, int Cin, int ntaps, const void* X, int Cin2, const void* Wp,
                         int Npad, int wexp, const float* bias, int bias_bstride, const float* residual, int div_sqrt2,
                         float* out, int Cout, int ldc, int B, int H, int W, int impl, void* stream);

@@ -131,3 +131,22 @@ def test_conv_gemm_simt(ctx, case):
 def test_conv_gemm_tcgen05(ctx, case):
     err, scale = _conv_case(ctx, case, impl=0)
     assert err < 2e-5 * max(1.0, scale), (err, scale)
+
+
+HALO_CASES = [
+    # B, H, W, Cin, Cout, ntaps, Cin2, residual, div       (halo kernel: 3x3, H % 16 == 0, W % 8 == 0)
+    (1, 16, 8, 128, 128, 9, 0, True, True),                # one tile, image == tile (all four borders padded)
+    (1, 16, 40, 128, 256, 9, 0, False, False),             # two N tiles
+    (1, 32, 64, 384, 128, 9, 384, False, True),            # folded 1x1 shortcut chunks
+    (2, 16, 8, 256, 4, 9, 0, False, False),                # pyramid head (BN = 16), batch 2
+    (1, 128, 160, 64, 128, 9, 0, True, True),              # 160 tiles > 148 CTAs: persistent loop, TMEM double buffer
+    (2, 64, 96, 128, 256, 9, 128, False, True),            # 192 tiles, shortcut, batch 2
+]
+
+
+@pytest.mark.parametrize("impl", [2, 3])
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv_halo(ctx, case, impl):
+    """impl 2: halo kernel with one main accumulator (double-buffered TMEM); impl 3: three rotating main accumulators."""
+    err, scale = _conv_case(ctx, case, impl=impl)
+    assert err < 2e-5 * max(1.0, scale), (err, scale)
