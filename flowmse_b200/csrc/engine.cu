@@ -868,6 +868,7 @@ int flowse_debug_tap(flowse_ctx* ctx, int module_idx, const float** ptr, int* C,
 static int ensure_op_stats(flowse_ctx* ctx) {
   if (ctx->op_stats) return 0;
   CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_stats), 2 * 64 * kStatSlotDoubles * sizeof(double)));   // two sources
+  CK(cudaMemset(ctx->op_stats, 0, 2 * 64 * kStatSlotDoubles * sizeof(double)));   // quad_stats fills replica 0 only
   CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_partials), static_cast<size_t>(64) * gn_stats_max_blocks() * 256 * sizeof(double)));
   CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_counters), 64 * sizeof(unsigned)));
   CK(cudaMemset(ctx->op_counters, 0, 64 * sizeof(unsigned)));
@@ -903,6 +904,8 @@ int flowse_op_gn_prep(flowse_ctx* ctx, const float* src1, int C1, const float* s
   if (B > 64) { ctx->err = "gn_prep op: B <= 64"; return 2; }
   if (int rc = ensure_op_stats(ctx)) return rc;
   double* qs2 = ctx->op_stats + static_cast<size_t>(64) * kStatSlotDoubles;
+  // the slot layout depends on the channel count: clear what an earlier call with another shape left in the replicas
+  CK(cudaMemsetAsync(ctx->op_stats, 0, 2 * 64 * kStatSlotDoubles * sizeof(double), s));
   launch_quad_stats(src1, C1, B, H * W, ctx->op_stats, ctx->op_partials, ctx->op_counters, s);
   if (src2) launch_quad_stats(src2, C2, B, H * W, qs2, ctx->op_partials, ctx->op_counters, s);
   PrepArgs pa{};
@@ -959,6 +962,7 @@ int flowse_op_attention(flowse_ctx* ctx, int module_idx, const float* x, float* 
   float* qkv = hn + static_cast<size_t>(B) * L * C;
   float* O = qkv + static_cast<size_t>(B) * L * 3 * C;
   float* S = O + static_cast<size_t>(B) * L * C;
+  CK(cudaMemsetAsync(ctx->op_stats, 0, 2 * 64 * kStatSlotDoubles * sizeof(double), s));
   launch_quad_stats(x, C, B, L, ctx->op_stats, ctx->op_partials, ctx->op_counters, s);
   PrepArgs pa{};
   pa.src1 = x; pa.C1 = C; pa.qs1 = ctx->op_stats; pa.gamma = a.gn_g; pa.beta = a.gn_b; pa.B = B; pa.H = H; pa.W = W;

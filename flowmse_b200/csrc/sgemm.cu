@@ -1,85 +1,180 @@
 // Small batched fp32 SIMT GEMM used by the four attention blocks of NCSN++ (0.15 % of the FLOPs per NFE):
 // q/k/v projections (NIN, /root/reference/flowmse/backbones/ncsnpp_utils/layers.py:546-555), q.k^T scores,
 // softmax(scores).v and the NIN_3 output projection with the residual epilogue (layerspp.py:75-91).
-// Exact fp32 FMA arithmetic; 64x64 tile, K step 16, 256 threads, 4x4 register micro-tile.
+// Exact fp32 FMA arithmetic (these products feed a softmax: no operand splitting, no tensor cores).
+//
+// TM x 64 tile (TM = 64 or 32, picked so that the few-hundred-token problems still fill the GPU), K step 32,
+// 256 threads, (TM/16) x 4 register micro-tile.  Operands are staged k-major in shared memory so that the inner loop
+// is two 16-byte shared loads per 4 x 4 FMAs; the next K step's global loads are issued into registers before the
+// current step is computed (the problems are latency-bound: K <= 512).
 #include "flowse_internal.h"
 
 namespace flowse {
 
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TN = 64, TK = 32, LDS_PAD = 4;
 
+template <int TM>
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const SgemmArgs a) {
-  __shared__ float sA[TK][TM + 4];
-  __shared__ float sB[TK][TN + 4];
+  constexpr int RM = TM / 16;                         // rows per thread
+  constexpr int A_F4 = TM * TK / 4 / 256;             // float4 loads of A per thread per K step (2 or 1)
+  constexpr int B_F4 = TN * TK / 4 / 256;             // 2
+  __shared__ __align__(16) float sA[TK][TM + LDS_PAD];
+  __shared__ __align__(16) float sB[TK][TN + LDS_PAD];
   const int bz = blockIdx.z;
-  const float* A = a.A + bz * a.strideA;
-  const float* Bm = a.Bm + bz * a.strideB;
-  float* C = a.C + bz * a.strideC;
-  const float* R = a.residual ? a.residual + bz * a.strideR : nullptr;
+  const float* __restrict__ A = a.A + bz * a.strideA;
+  const float* __restrict__ Bm = a.Bm + bz * a.strideB;
+  float* __restrict__ C = a.C + bz * a.strideC;
+  const float* __restrict__ R = a.residual ? a.residual + bz * a.strideR : nullptr;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;        // 16 x 16 threads, each 4 rows x 4 cols
-  float acc[4][4] = {};
+  const int tx = tid & 15, ty = tid >> 4;
+  const bool vecA = (a.lda % 4 == 0) && ((reinterpret_cast<size_t>(A) & 15) == 0);
+  const bool vecB = (a.ldb % 4 == 0) && ((reinterpret_cast<size_t>(Bm) & 15) == 0);
+
+  float4 ra[A_F4], rb[B_F4];
+  // A tile: TM rows x 32 k, row-major in global: float4 f -> row f / 8, k4 = f % 8
+  auto load_a = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < A_F4; ++i) {
+      const int f = tid + i * 256;
+      const int r = f >> 3, k = k0 + ((f & 7) << 2);
+      const int m = m0 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < a.M) {
+        const float* src = A + static_cast<size_t>(m) * a.lda + k;
+        if (vecA && k + 3 < a.K) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          if (k < a.K) v.x = __ldg(src);
+          if (k + 1 < a.K) v.y = __ldg(src + 1);
+          if (k + 2 < a.K) v.z = __ldg(src + 2);
+          if (k + 3 < a.K) v.w = __ldg(src + 3);
+        }
+      }
+      ra[i] = v;
+    }
+  };
+  auto store_a = [&]() {
+#pragma unroll
+    for (int i = 0; i < A_F4; ++i) {
+      const int f = tid + i * 256;
+      const int r = f >> 3, k = (f & 7) << 2;
+      sA[k][r] = ra[i].x; sA[k + 1][r] = ra[i].y; sA[k + 2][r] = ra[i].z; sA[k + 3][r] = ra[i].w;
+    }
+  };
+  // B tile: transB ? [N][K] (float4 along k, stored transposed) : [K][N] (float4 along n, stored as is)
+  auto load_b = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < B_F4; ++i) {
+      const int f = tid + i * 256;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.transB) {
+        const int c = f >> 3, k = k0 + ((f & 7) << 2);
+        const int n = n0 + c;
+        if (n < a.N) {
+          const float* src = Bm + static_cast<size_t>(n) * a.ldb + k;
+          if (vecB && k + 3 < a.K) v = __ldg(reinterpret_cast<const float4*>(src));
+          else {
+            if (k < a.K) v.x = __ldg(src);
+            if (k + 1 < a.K) v.y = __ldg(src + 1);
+            if (k + 2 < a.K) v.z = __ldg(src + 2);
+            if (k + 3 < a.K) v.w = __ldg(src + 3);
+          }
+        }
+      } else {
+        const int kk = f >> 4, n = n0 + ((f & 15) << 2);
+        const int k = k0 + kk;
+        if (k < a.K) {
+          const float* src = Bm + static_cast<size_t>(k) * a.ldb + n;
+          if (vecB && n + 3 < a.N) v = __ldg(reinterpret_cast<const float4*>(src));
+          else {
+            if (n < a.N) v.x = __ldg(src);
+            if (n + 1 < a.N) v.y = __ldg(src + 1);
+            if (n + 2 < a.N) v.z = __ldg(src + 2);
+            if (n + 3 < a.N) v.w = __ldg(src + 3);
+          }
+        }
+      }
+      rb[i] = v;
+    }
+  };
+  auto store_b = [&]() {
+#pragma unroll
+    for (int i = 0; i < B_F4; ++i) {
+      const int f = tid + i * 256;
+      if (a.transB) {
+        const int c = f >> 3, k = (f & 7) << 2;
+        sB[k][c] = rb[i].x; sB[k + 1][c] = rb[i].y; sB[k + 2][c] = rb[i].z; sB[k + 3][c] = rb[i].w;
+      } else {
+        const int kk = f >> 4, c = (f & 15) << 2;
+        *reinterpret_cast<float4*>(&sB[kk][c]) = rb[i];
+      }
+    }
+  };
+
+  float acc[RM][4] = {};
+  load_a(0); load_b(0);
   for (int k0 = 0; k0 < a.K; k0 += TK) {
-    // A tile: 64 rows x 16 k
-    for (int i = tid; i < TM * TK; i += 256) {
-      const int r = i / TK, kk = i % TK;
-      const int m = m0 + r, k = k0 + kk;
-      sA[kk][r] = (m < a.M && k < a.K) ? A[static_cast<size_t>(m) * a.lda + k] : 0.f;
-    }
-    if (a.transB) {   // B given as [N][K]
-      for (int i = tid; i < TN * TK; i += 256) {
-        const int c = i / TK, kk = i % TK;
-        const int n = n0 + c, k = k0 + kk;
-        sB[kk][c] = (n < a.N && k < a.K) ? Bm[static_cast<size_t>(n) * a.ldb + k] : 0.f;
-      }
-    } else {          // B given as [K][N]
-      for (int i = tid; i < TN * TK; i += 256) {
-        const int kk = i / TN, c = i % TN;
-        const int n = n0 + c, k = k0 + kk;
-        sB[kk][c] = (n < a.N && k < a.K) ? Bm[static_cast<size_t>(k) * a.ldb + n] : 0.f;
-      }
-    }
+    store_a(); store_b();
     __syncthreads();
+    if (k0 + TK < a.K) { load_a(k0 + TK); load_b(k0 + TK); }      // in flight while this step is computed
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
-      float av[4], bv[4];
+      float av[RM];
+      if constexpr (RM == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);
+        av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+      } else {
+        const float2 v = *reinterpret_cast<const float2*>(&sA[kk][ty * 2]);
+        av[0] = v.x; av[1] = v.y;
+      }
+      const float4 bv = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = sA[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = sB[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int i = 0; i < RM; ++i) {
+        acc[i][0] = fmaf(av[i], bv.x, acc[i][0]); acc[i][1] = fmaf(av[i], bv.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i], bv.z, acc[i][2]); acc[i][3] = fmaf(av[i], bv.w, acc[i][3]);
+      }
     }
     __syncthreads();
   }
+  const bool vecC = (a.ldc % 4 == 0) && ((reinterpret_cast<size_t>(C) & 15) == 0) &&
+                    (!R || ((a.ldr % 4 == 0) && ((reinterpret_cast<size_t>(R) & 15) == 0)));
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < RM; ++i) {
+    const int m = m0 + ty * RM + i;
     if (m >= a.M) continue;
+    const int n = n0 + tx * 4;
+    float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n >= a.N) continue;
-      float v = acc[i][j] * a.alpha;
-      if (a.bias) v += a.bias[n];
-      if (R) v = R[static_cast<size_t>(m) * a.ldr + n] + v;
-      if (a.div_sqrt2) v = __fdiv_rn(v, kSqrt2);
-      C[static_cast<size_t>(m) * a.ldc + n] = v;
+      v[j] = acc[i][j] * a.alpha;
+      if (n + j < a.N) {
+        if (a.bias) v[j] += a.bias[n + j];
+        if (R) v[j] = R[static_cast<size_t>(m) * a.ldr + n + j] + v[j];
+        if (a.div_sqrt2) v[j] = __fdiv_rn(v[j], kSqrt2);
+      }
     }
+    float* dst = C + static_cast<size_t>(m) * a.ldc + n;
+    if (vecC && n + 3 < a.N) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    else
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (n + j < a.N) dst[j] = v[j];
   }
 }
 
 }  // namespace
 
 void launch_sgemm(const SgemmArgs& a, cudaStream_t s) {
-  dim3 grid((a.N + TN - 1) / TN, (a.M + TM - 1) / TM, a.batch);
-  sgemm_kernel<<<grid, 256, 0, s>>>(a);
+  const long long tiles64 = static_cast<long long>((a.N + TN - 1) / TN) * ((a.M + 63) / 64) * a.batch;
+  if (tiles64 >= 120 && a.M > 32) {
+    dim3 grid((a.N + TN - 1) / TN, (a.M + 63) / 64, a.batch);
+    sgemm_kernel<64><<<grid, 256, 0, s>>>(a);
+  } else {
+    dim3 grid((a.N + TN - 1) / TN, (a.M + 31) / 32, a.batch);
+    sgemm_kernel<32><<<grid, 256, 0, s>>>(a);
+  }
   ++launch_counter();
 }
 
