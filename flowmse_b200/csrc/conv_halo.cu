@@ -17,6 +17,13 @@
 //    (2 buffers x {main, correction} x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
 //  * Warp roles: warp 0 TMA producer (A halos + B blocks), warp 1 MMA issuer, warp 2 TMEM allocator,
 //    warps 4..11 epilogue (two per TMEM lane quadrant).
+//  * PAIR variant (Cout tiles of 128): two CTAs of a cluster (one TPC) work on two M tiles with the same weights as ONE
+//    tcgen05.mma.cta_group::2 of shape 256 x 128 x 16.  Each CTA stages its own A halo and only HALF of the B block
+//    (64 of the 128 weight rows); the tensor cores read the other half from the peer's shared memory.  With the halo
+//    the weight stream is what is left of the L2->SM traffic, so this halves the remaining bytes per MMA.
+//    Protocol: both CTAs' TMA loads complete on the LEADER's full barriers (cta_group::2 form, leader arms the
+//    transaction count for both), the leader's MMA warp issues for the pair and multicasts its commits to both CTAs'
+//    empty / accumulator-full barriers, both epilogues arrive on the leader's accumulator-empty barrier.
 #include "flowse_internal.h"
 #include "ptx.cuh"
 
@@ -44,17 +51,18 @@ constexpr int NUM_THREADS = 384;
 constexpr int kEpiWarps = 8;
 constexpr int kFirstEpiWarp = 4;
 
-template <int BN, int NMAIN>
+template <int BN, int NMAIN, bool PAIR>
 struct HCfg {
-  static constexpr int B_PLANE = BN * 128;
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;               // weight rows staged by this CTA
+  static constexpr int B_PLANE = B_ROWS * 128;
   static constexpr int B_STAGE_BYTES = 2 * B_PLANE;
-  static constexpr int B_STAGES = (BN >= 128) ? 3 : 8;
+  static constexpr int B_STAGES = (BN >= 128) ? (PAIR ? 6 : 3) : 8;
   static constexpr int SLOT_COLS = (BN < 32) ? 32 : BN;
   static constexpr int NSLOT = NMAIN + 1;                          // hi*hi chains + one correction accumulator
   static constexpr int NBUF = (NSLOT * SLOT_COLS * 2 <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS_RAW = NBUF * NSLOT * SLOT_COLS;
-  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
-                                   : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static constexpr int TMEM_COLS = PAIR ? 512 : TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64
+                                   : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int CH = 16;
   static constexpr int STG_STRIDE = CH + 4;
   static constexpr int STG_BYTES = kEpiWarps * 32 * STG_STRIDE * 4;
@@ -63,7 +71,7 @@ struct HCfg {
 };
 
 struct HaloParams {
-  int H, W, tiles_w, tiles_h, n_tiles, num_tiles;
+  int H, W, tiles_w, tiles_h, n_tiles, num_items;   // items = tiles (single CTA) or pairs of M tiles (PAIR)
   int nchunk_main, nchunk_sc;
   int Cout, ldc;
   float wscale_inv;
@@ -77,11 +85,13 @@ struct HaloParams {
 
 struct TileCoord { int b, h0, w0, n0; };
 
-template <int BN>
-__device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int tile) {
+// work item -> output tile of this CTA.  PAIR: item = (pair of adjacent M tiles, N tile); CTA rank r takes M tile 2*pm + r.
+template <int BN, bool PAIR>
+__device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int item, int rank) {
   TileCoord t;
-  const int nt = tile % p.n_tiles;
-  int m = tile / p.n_tiles;
+  const int nt = item % p.n_tiles;
+  int m = item / p.n_tiles;
+  if (PAIR) m = 2 * m + rank;
   const int per_img = p.tiles_w * p.tiles_h;
   t.b = m / per_img;
   m -= t.b * per_img;
@@ -101,15 +111,68 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in the executing CTA, the transaction bytes complete on `bar`, which may live in
+// the peer (leader) CTA
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (once the issuing thread's MMAs have retired) on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int BN, int NMAIN>
+template <int BN, int NMAIN, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX,
                  const __grid_constant__ CUtensorMap tmW, const HaloParams p) {
-  using C = HCfg<BN, NMAIN>;
+  using C = HCfg<BN, NMAIN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   constexpr int NBARS = 2 * A_STAGES + 2 * C::B_STAGES + 2 * C::NBUF;
   __shared__ uint64_t bars[NBARS];
@@ -132,6 +195,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nchunks = p.nchunk_main + p.nchunk_sc;
+  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int item0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int item_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  constexpr int kCtas = PAIR ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -139,15 +206,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::prefetch_tensormap(&tmW);
     for (int s = 0; s < A_STAGES; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
     for (int s = 0; s < C::B_STAGES; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < C::NBUF; ++s) { ptx::mbar_init(t_full(s), 1); ptx::mbar_init(t_empty(s), kEpiWarps); }
+    for (int s = 0; s < C::NBUF; ++s) { ptx::mbar_init(t_full(s), 1); ptx::mbar_init(t_empty(s), kEpiWarps * kCtas); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
-    ptx::tmem_relinquish();
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+    else { ptx::tmem_alloc(tmem_slot, C::TMEM_COLS); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot_ptr;
 
@@ -156,21 +224,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      auto issue_A = [&](int tile, int c) {
-        const TileCoord t = decode_tile<BN>(p, tile);
+      // PAIR: the full barriers that count are the leader's; this CTA's loads complete there
+      auto full_addr = [&](uint32_t local) { return PAIR ? map_to_cta(local, 0) : local; };
+      auto issue_A = [&](int item, int c) {
+        const TileCoord t = decode_tile<BN, PAIR>(p, item, rank);
         ptx::mbar_wait(a_empty(as), aph ^ 1u);
-        ptx::mbar_expect_tx(a_full(as), 2 * A_PLANE_BYTES);
+        if (rank == 0) ptx::mbar_expect_tx(a_full(as), 2 * A_PLANE_BYTES * kCtas);
         const bool main = c < p.nchunk_main;
         const CUtensorMap* m = main ? &tmA : &tmX;
         const int ch = main ? c : c - p.nchunk_main;
-        ptx::tma_load_5d(m, a_full(as), sA(as), ch * BK, t.w0 - 1, t.h0 - 1, t.b, 0);
-        ptx::tma_load_5d(m, a_full(as), sA(as) + A_PLANE_STRIDE, ch * BK, t.w0 - 1, t.h0 - 1, t.b, 1);
+        const uint32_t bar = full_addr(a_full(as));
+        if constexpr (PAIR) {
+          tma_load_5d_pair(m, bar, sA(as), ch * BK, t.w0 - 1, t.h0 - 1, t.b, 0);
+          tma_load_5d_pair(m, bar, sA(as) + A_PLANE_STRIDE, ch * BK, t.w0 - 1, t.h0 - 1, t.b, 1);
+        } else {
+          ptx::tma_load_5d(m, bar, sA(as), ch * BK, t.w0 - 1, t.h0 - 1, t.b, 0);
+          ptx::tma_load_5d(m, bar, sA(as) + A_PLANE_STRIDE, ch * BK, t.w0 - 1, t.h0 - 1, t.b, 1);
+        }
         if (++as == A_STAGES) { as = 0; aph ^= 1u; }
       };
-      int tile = blockIdx.x;
-      if (tile < p.num_tiles) issue_A(tile, 0);
-      for (; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile<BN>(p, tile);
+      int item = item0;
+      if (item < p.num_items) issue_A(item, 0);
+      for (; item < p.num_items; item += item_stride) {
+        const TileCoord t = decode_tile<BN, PAIR>(p, item, rank);
+        const int brow = t.n0 + rank * C::B_ROWS;       // PAIR: this CTA stages its half of the weight rows
         for (int c = 0; c < nchunks; ++c) {
           const bool main = c < p.nchunk_main;
           const int ntap = main ? 9 : 1;
@@ -178,26 +255,51 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int tp = 0; tp < ntap; ++tp) {
             const int kb = main ? tp * p.nchunk_main + c : 9 * p.nchunk_main + (c - p.nchunk_main);
             ptx::mbar_wait(b_empty(bs), bph ^ 1u);
-            ptx::mbar_expect_tx(b_full(bs), C::B_STAGE_BYTES);
-            ptx::tma_load_3d(&tmW, b_full(bs), sB(bs), kb * BK, t.n0, 0);
-            ptx::tma_load_3d(&tmW, b_full(bs), sB(bs) + C::B_PLANE, kb * BK, t.n0, 1);
+            if (rank == 0) ptx::mbar_expect_tx(b_full(bs), C::B_STAGE_BYTES * kCtas);
+            const uint32_t bar = full_addr(b_full(bs));
+            if constexpr (PAIR) {
+              tma_load_3d_pair(&tmW, bar, sB(bs), kb * BK, brow, 0);
+              tma_load_3d_pair(&tmW, bar, sB(bs) + C::B_PLANE, kb * BK, brow, 1);
+            } else {
+              ptx::tma_load_3d(&tmW, bar, sB(bs), kb * BK, brow, 0);
+              ptx::tma_load_3d(&tmW, bar, sB(bs) + C::B_PLANE, kb * BK, brow, 1);
+            }
             if (++bs == C::B_STAGES) { bs = 0; bph ^= 1u; }
             if (tp == pre) {
-              if (c + 1 < nchunks) issue_A(tile, c + 1);
-              else if (tile + static_cast<int>(gridDim.x) < p.num_tiles) issue_A(tile + gridDim.x, 0);
+              if (c + 1 < nchunks) issue_A(item, c + 1);
+              else if (item + item_stride < p.num_items) issue_A(item + item_stride, 0);
             }
           }
+        }
+      }
+      if constexpr (PAIR) {
+        // drain: every multicast commit aimed at this CTA's empty barriers has landed before the CTA may exit
+        for (int i = 0; i < C::B_STAGES; ++i) {
+          ptx::mbar_wait(b_empty(bs), bph ^ 1u);
+          if (++bs == C::B_STAGES) { bs = 0; bph ^= 1u; }
+        }
+        for (int i = 0; i < A_STAGES; ++i) {
+          ptx::mbar_wait(a_empty(as), aph ^ 1u);
+          if (++as == A_STAGES) { as = 0; aph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(BM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(BM * kCtas, BN);
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc_flag) {
+        if constexpr (PAIR) mma_f16_ss_pair(d, da, db, idesc, acc_flag);
+        else ptx::mma_f16_ss(d, da, db, idesc, acc_flag);
+      };
+      auto commit = [&](uint32_t bar) {
+        if constexpr (PAIR) mma_commit_pair(bar);
+        else ptx::mma_commit(bar);
+      };
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int item = item0; item < p.num_items; item += item_stride, ++it) {
         const int buf = it % C::NBUF;
         const uint32_t use = static_cast<uint32_t>(it / C::NBUF);
         ptx::mbar_wait(t_empty(buf), (use & 1u) ^ 1u);        // epilogue has drained this accumulator buffer
@@ -226,17 +328,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint64_t dB_hi = make_desc_sw128(b_hi + koff, 1024);
               const uint64_t dB_lo = make_desc_sw128(b_lo + koff, 1024);
               const uint32_t d_main = acc + static_cast<uint32_t>((ks % NMAIN) * C::SLOT_COLS);
-              ptx::mma_f16_ss(d_main, dA_hi, dB_hi, idesc, ks >= NMAIN ? 1u : 0u);
-              ptx::mma_f16_ss(d_corr, dA_hi, dB_lo, idesc, ks > 0 ? 1u : 0u);
-              ptx::mma_f16_ss(d_corr, dA_lo, dB_hi, idesc, 1u);
+              mma(d_main, dA_hi, dB_hi, ks >= NMAIN ? 1u : 0u);
+              mma(d_corr, dA_hi, dB_lo, ks > 0 ? 1u : 0u);
+              mma(d_corr, dA_lo, dB_hi, 1u);
             }
-            ptx::mma_commit(b_empty(bs));
+            commit(b_empty(bs));
             if (++bs == C::B_STAGES) { bs = 0; bph ^= 1u; }
           }
-          ptx::mma_commit(a_empty(as));
+          commit(a_empty(as));
           if (++as == A_STAGES) { as = 0; aph ^= 1u; }
         }
-        ptx::mma_commit(t_full(buf));
+        commit(t_full(buf));
       }
     }
   } else if (warp >= kFirstEpiWarp) {
@@ -261,10 +363,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const float post = p.div_sqrt2 ? 0.70710678118654752440f : 1.0f;
     const int etid = threadIdx.x - kFirstEpiWarp * 32;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const TileCoord t = decode_tile<BN>(p, tile);
+    for (int item = item0; item < p.num_items; item += item_stride, ++it) {
+      const TileCoord t = decode_tile<BN, PAIR>(p, item, rank);
+      const int tile = PAIR ? 2 * item + rank : item;         // spreads the statistics atomics over the replicas
       const int buf = it % C::NBUF;
       const uint32_t use = static_cast<uint32_t>(it / C::NBUF);
+      // the accumulator-empty barrier that counts is the leader's
+      const uint32_t t_empty_bar = (PAIR && rank != 0) ? map_to_cta(t_empty(buf), 0) : t_empty(buf);
+      auto release_tmem = [&]() {
+        if constexpr (PAIR) { if (rank != 0) mbar_arrive_cluster(t_empty_bar); else ptx::mbar_arrive(t_empty_bar); }
+        else ptx::mbar_arrive(t_empty_bar);
+      };
       const float* brow = p.bias + static_cast<size_t>(t.b) * p.bias_bstride;
       long long off[NIT];
 #pragma unroll
@@ -312,7 +421,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // all TMEM reads of this warp for this tile are complete: hand the buffer back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(t_empty(buf));
+            if (lane == 0) release_tmem();
           } else {
             __syncwarp();
           }
@@ -360,7 +469,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else {
         // inactive half (BN < 32): it has waited for t_full like everyone else, so its arrival belongs to this phase
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(t_empty(buf));
+        if (lane == 0) release_tmem();
       }
       if (p.qstats) {
         // fold the four quadrant warps of each column half in a fixed order, then one fp64 atomic pair per quad
@@ -385,9 +494,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();      // neither CTA's shared memory / TMEM goes away while the peer may touch it
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_acc, C::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_acc, C::TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_acc, C::TMEM_COLS);
   }
 }
 
@@ -460,12 +571,12 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int NMAIN>
+template <int BN, int NMAIN, bool PAIR>
 int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
-  using C = HCfg<BN, NMAIN>;
+  using C = HCfg<BN, NMAIN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, NMAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, NMAIN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(halo): ") + cudaGetErrorString(e); return 1; }
     attr_set = true;
@@ -474,7 +585,8 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   p.H = a.H; p.W = a.W;
   p.tiles_w = a.W / TW; p.tiles_h = a.H / TH;
   p.n_tiles = (a.Cout + BN - 1) / BN;
-  p.num_tiles = a.B * p.tiles_w * p.tiles_h * p.n_tiles;
+  const int m_tiles = a.B * p.tiles_w * p.tiles_h;
+  p.num_items = (PAIR ? m_tiles / 2 : m_tiles) * p.n_tiles;
   p.nchunk_main = a.Cin / BK;
   p.nchunk_sc = a.X ? a.Cin2 / BK : 0;
   p.Cout = a.Cout; p.ldc = a.ldc; p.wscale_inv = a.wscale_inv;
@@ -485,11 +597,24 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   if (!make_halo_map(&tmA, a.A, a.B, a.H, a.W, a.Cin, err)) return 1;
   if (a.X) { if (!make_halo_map(&tmX, a.X, a.B, a.H, a.W, a.Cin2, err)) return 1; }
   else tmX = tmA;
-  if (!make_w_map(&tmW, a.Wp, a.Npad, K, BN, err)) return 1;
-  const int grid = std::min(p.num_tiles, num_sms());
-  conv_halo_kernel<BN, NMAIN><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(tmA, tmX, tmW, p);
+  if (!make_w_map(&tmW, a.Wp, a.Npad, K, C::B_ROWS, err)) return 1;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = s;
+  if (PAIR) {
+    const int clusters = std::min(p.num_items, num_sms() / 2);
+    cfg.gridDim = dim3(2 * clusters);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(std::min(p.num_items, num_sms()));
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, NMAIN, PAIR>, tmA, tmX, tmW, p);
   ++launch_counter();
-  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv_halo launch: ") + cudaGetErrorString(e); return 1; }
   return 0;
 }
@@ -501,10 +626,16 @@ bool conv_halo_supported(const ConvGemmArgs& a) {
          (a.Npad % 128 == 0 || a.Npad == 16);
 }
 
-int launch_conv_halo(const ConvGemmArgs& a, int nmain, cudaStream_t s, std::string* err) {
+// variant: 1 = one main accumulator (double-buffered TMEM), 3 = three rotating main accumulators,
+//          2 = CTA pairs (cta_group::2, one main accumulator, double-buffered TMEM); falls back to 1 when unavailable
+int launch_conv_halo(const ConvGemmArgs& a, int variant, cudaStream_t s, std::string* err) {
   if (!conv_halo_supported(a)) { if (err) *err = "conv_halo: unsupported shape"; return 1; }
-  if (a.Npad % 128 == 0) return nmain == 3 ? launch_halo<128, 3>(a, s, err) : launch_halo<128, 1>(a, s, err);
-  return nmain == 3 ? launch_halo<16, 3>(a, s, err) : launch_halo<16, 1>(a, s, err);
+  if (a.Npad % 128 == 0) {
+    const int m_tiles = a.B * (a.W / TW) * (a.H / TH);
+    if (variant == 2 && m_tiles % 2 == 0) return launch_halo<128, 1, true>(a, s, err);
+    return variant == 3 ? launch_halo<128, 3, false>(a, s, err) : launch_halo<128, 1, false>(a, s, err);
+  }
+  return variant == 3 ? launch_halo<16, 3, false>(a, s, err) : launch_halo<16, 1, false>(a, s, err);
 }
 
 }  // namespace flowse

@@ -323,14 +323,15 @@ struct Arena {
 };
 
 // conv_impl: 0 = auto (halo kernel for the high-resolution layers, per-tap kernel otherwise), 1 = SIMT cross-check,
-// 2 = per-tap tcgen05 kernel everywhere, 3 = auto with 3 rotating main accumulators in the halo kernel.
+// 2 = per-tap tcgen05 kernel everywhere, 3 = auto with 3 rotating main accumulators in the halo kernel,
+// 4 = auto with the CTA-pair (cta_group::2) halo kernel.
 int run_conv(flowse_ctx* ctx, const ConvGemmArgs& a, cudaStream_t s) {
   std::string e;
   int rc;
   if (ctx->conv_impl == 1) rc = launch_conv_gemm_simt(a, s, &e);
   else if (ctx->conv_impl != 2 && conv_halo_supported(a) &&
            static_cast<long long>(a.B) * (a.H / 16) * (a.W / 8) * ((a.Cout + 127) / 128) >= 100)
-    rc = launch_conv_halo(a, ctx->conv_impl == 3 ? 3 : 1, s, &e);
+    rc = launch_conv_halo(a, ctx->conv_impl == 3 ? 3 : (ctx->conv_impl == 4 ? 2 : 1), s, &e);
   else rc = launch_conv_gemm(a, s, &e);
   if (rc) ctx->err = e;
   return rc;
@@ -933,7 +934,7 @@ int flowse_op_conv_gemm(flowse_ctx* ctx, const void* A, int Cin, int ntaps, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
   if (impl == 1) rc = launch_conv_gemm_simt(a, st, &e);
-  else if (impl == 2 || impl == 3) rc = launch_conv_halo(a, impl == 3 ? 3 : 1, st, &e);   // halo kernel, 1 / 3 main slots
+  else if (impl >= 2 && impl <= 4) rc = launch_conv_halo(a, impl == 3 ? 3 : (impl == 4 ? 2 : 1), st, &e);   // halo kernel
   else rc = launch_conv_gemm(a, st, &e);
   if (rc) ctx->err = e;
   return rc;

@@ -76,7 +76,8 @@ int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const voi
                   float sigma, void* x_out, int B, int T, void* stream);
 
 /* Options: "conv_impl" 0 = tcgen05 (default: halo kernel on high-resolution layers, per-tap kernel otherwise),
- * 1 = SIMT cross-check, 2 = per-tap kernel everywhere, 3 = like 0 with 3 rotating main accumulators in the halo kernel; "graph" 0/1 = replay each NFE as a CUDA graph. */
+ * 1 = SIMT cross-check, 2 = per-tap kernel everywhere, 3 = like 0 with 3 rotating main accumulators in the halo kernel,
+ * 4 = like 0 with the CTA-pair (cta_group::2) halo kernel; "graph" 0/1 = replay each NFE as a CUDA graph. */
 int flowse_set_option(flowse_ctx* ctx, const char* key, int value);
 
 /* Number of this library's kernel launches (graph kernel nodes included) since the context was created. */
@@ -108,7 +109,8 @@ int flowse_op_gn_prep(flowse_ctx* ctx, const float* src1, int C1, const float* s
                       float* outXF, void* stream);
 
 /* Implicit-GEMM conv (3x3 pad 1 when ntaps == 9, 1x1 when 1) on hi/lo operands; impl 0 = per-tap tcgen05 kernel,
- * 1 = SIMT cross-check, 2 / 3 = halo tcgen05 kernel (3x3, H % 16 == 0, W % 8 == 0) with 1 / 3 main accumulators. */
+ * 1 = SIMT cross-check, 2 / 3 = halo tcgen05 kernel (3x3, H % 16 == 0, W % 8 == 0) with 1 / 3 main accumulators,
+ * 4 = halo kernel on CTA pairs (cta_group::2). */
 int flowse_op_conv_gemm(flowse_ctx* ctx, const void* A, int Cin, int ntaps, const void* X, int Cin2, const void* Wp,
                         int Npad, int wexp, const float* bias, int bias_bstride, const float* residual, int div_sqrt2,
                         float* out, int Cout, int ldc, int B, int H, int W, int impl, void* stream);

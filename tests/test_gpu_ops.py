@@ -144,10 +144,11 @@ HALO_CASES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [2, 3])
+@pytest.mark.parametrize("impl", [2, 3, 4])
 @pytest.mark.parametrize("case", HALO_CASES)
 def test_conv_halo(ctx, case, impl):
-    """impl 2: halo kernel with one main accumulator (double-buffered TMEM); impl 3: three rotating main accumulators."""
+    """impl 2: halo kernel with one main accumulator (double-buffered TMEM); impl 3: three rotating main accumulators;
+    impl 4: CTA pairs (tcgen05.mma.cta_group::2, each CTA stages half of the weight block)."""
     err, scale = _conv_case(ctx, case, impl=impl)
     assert err < 2e-5 * max(1.0, scale), (err, scale)
 
