@@ -22,6 +22,10 @@ import sys
 import threading
 import time
 
+# NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION (this image's default); stdout carries the JSON line only
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -119,6 +123,7 @@ def run_reference_arm(args):
         return
     from flowmse_b200.checkpoint import synthetic_state_dict
     torch.set_grad_enabled(False)
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     sd = synthetic_state_dict(0)
     cores = torch.get_num_threads()
     T_s = 128                                   # bounded sample: the first 128 of the workload's 512 frames per step
@@ -286,8 +291,9 @@ def run_ours(args):
                                     "bytes_per_bin": 24, "sample": "32 Mi bins (768 MiB traffic per launch, > L2)"}
         del xa, va
         # ---- CPU baseline (oracle port) on a bounded sample ------------------------------------------------------
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             sd = synthetic_state_dict(0)
+            torch.set_num_threads(os.cpu_count() or 1)
             cores = torch.get_num_threads()
             cpu_sampler_seconds(sd, 64, 1)                       # warm-up (thread pool, oneDNN primitives)
             secs = cpu_sampler_seconds(sd, 128, N_STEPS_ODE)
