@@ -96,6 +96,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const uint32_t tmem_slot = ptx::smem_u32(&tmem_slot_var);
   volatile uint32_t* tmem_slot_ptr = &tmem_slot_var;
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
@@ -136,6 +137,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot_ptr;
+  pdl_wait();                 // barriers, TMEM and tensor maps were set up while the previous kernel drained
   if (threadIdx.x == 0) stamp(1);
 
   if (warp == 0) {
@@ -343,6 +345,8 @@ splitk_reduce_kernel(const float* __restrict__ partial, int S, long long plane, 
                      int bias_bstride, const float* __restrict__ residual, float post, float* __restrict__ out,
                      int n4_per_batch, int ldc4, double* __restrict__ qstats) {
   __shared__ float ss[256], sq[256];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   float ls = 0.f, lq = 0.f;
@@ -383,6 +387,8 @@ splitk_reduce_kernel(const float* __restrict__ partial, int S, long long plane, 
 __global__ void conv_gemm_simt_kernel(const __half* __restrict__ A, const __half* __restrict__ X,
                                       const __half* __restrict__ Wp, int Cin, int Cin2, int ntaps, int Npad, int K,
                                       GemmParams p, int B) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t planeA = static_cast<size_t>(B) * p.H * p.W * Cin;
   const size_t planeX = static_cast<size_t>(B) * p.H * p.W * Cin2;
   const size_t planeW = static_cast<size_t>(Npad) * K;
@@ -571,8 +577,7 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   long long* dbuf = nullptr;
   const size_t ncta = static_cast<size_t>(grid.x) * grid.y;
   if (dbg) { cudaMalloc(&dbuf, ncta * 8 * sizeof(long long)); cudaMemset(dbuf, 0, ncta * 8 * sizeof(long long)); p.dbg = dbuf; }
-  conv_gemm_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(tmA, tmX, tmW, p);
-  ++launch_counter();
+  launch_k(conv_gemm_tcgen05_kernel<BN>, grid, dim3(NUM_THREADS), C::SMEM_BYTES, s, tmA, tmX, tmW, p);
   if (dbg) {
     cudaStreamSynchronize(s);
     std::vector<long long> h(ncta * 8);
@@ -592,10 +597,9 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
     const int n4b = a.H * a.W * a.ldc / 4;
     const bool can_stats = a.qstats && (256 % (a.ldc / 4) == 0);
     dim3 rgrid((n4b + 255) / 256, a.B);
-    splitk_reduce_kernel<<<rgrid, 256, 0, s>>>(p.partial, S, p.partial_plane, a.bias, a.bias_bstride, a.residual,
-                                               a.div_sqrt2 ? 0.70710678118654752440f : 1.0f, a.out, n4b, a.ldc / 4,
-                                               can_stats ? a.qstats : nullptr);
-    ++launch_counter();
+    launch_k(splitk_reduce_kernel, rgrid, dim3(256), 0, s, static_cast<const float*>(p.partial), S, p.partial_plane,
+             a.bias, a.bias_bstride, a.residual, a.div_sqrt2 ? 0.70710678118654752440f : 1.0f, a.out, n4b, a.ldc / 4,
+             can_stats ? a.qstats : static_cast<double*>(nullptr));
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv_gemm launch: ") + cudaGetErrorString(e); return 1; }
@@ -618,8 +622,8 @@ int launch_conv_gemm_simt(const ConvGemmArgs& a, cudaStream_t s, std::string* er
   const int K = a.ntaps * a.Cin + (a.X ? a.Cin2 : 0);
   const int threads = std::min(128, ((a.Cout + 31) / 32) * 32);
   dim3 grid(static_cast<unsigned>(static_cast<size_t>(a.B) * a.H * a.W), (a.Cout + threads - 1) / threads);
-  conv_gemm_simt_kernel<<<grid, threads, 0, s>>>(a.A, a.X, a.Wp, a.Cin, a.X ? a.Cin2 : 0, a.ntaps, a.Npad, K, p, a.B);
-  ++launch_counter();
+  launch_k(conv_gemm_simt_kernel, grid, dim3(threads), 0, s, a.A, a.X, a.Wp, a.Cin, a.X ? a.Cin2 : 0, a.ntaps, a.Npad, K, p,
+           a.B);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv_gemm_simt launch: ") + cudaGetErrorString(e); return 1; }
   return 0;

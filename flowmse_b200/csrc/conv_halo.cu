@@ -192,6 +192,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_slot = ptx::smem_u32(&tmem_slot_var);
   volatile uint32_t* tmem_slot_ptr = &tmem_slot_var;
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nchunks = p.nchunk_main + p.nchunk_sc;
@@ -218,6 +219,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot_ptr;
+  pdl_wait();                 // barriers, TMEM and tensor maps were set up while the previous kernel drained
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -599,16 +601,19 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   else tmX = tmA;
   if (!make_w_map(&tmW, a.Wp, a.Npad, K, C::B_ROWS, err)) return 1;
   cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = s;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
   if (PAIR) {
     const int clusters = std::min(p.num_items, num_sms() / 2);
     cfg.gridDim = dim3(2 * clusters);
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
   } else {
     cfg.gridDim = dim3(std::min(p.num_items, num_sms()));
   }

@@ -842,6 +842,7 @@ int flowse_set_option(flowse_ctx* ctx, const char* key, int value) {
   const std::string k(key);
   if (k == "conv_impl") ctx->conv_impl = value;
   else if (k == "graph") ctx->use_graph = value;
+  else if (k == "pdl") pdl_enabled() = (value != 0);
   else { ctx->err = "unknown option '" + k + "'"; return 2; }
   if (ctx->plan) {   // captured graphs bake the old setting
     cudaSetDevice(ctx->device);

@@ -11,6 +11,35 @@ namespace flowse {
 // Process-wide count of kernel launches issued by this library (incremented by every launch_* helper).
 long long& launch_counter();
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  One NFE is a chain of ~330 mostly short kernels; every kernel of the library
+//   1. calls pdl_launch_dependents() first: the NEXT kernel of the stream / graph may be scheduled as soon as all CTAs
+//      of this one are running, so its launch latency and input-independent prologue (barrier init, TMEM allocation,
+//      tensor-map prefetch, weight staging in registers) overlap this kernel;
+//   2. calls pdl_wait() before its first access to global memory another kernel may have produced or may still read
+//      (griddepcontrol.wait returns once all prerequisite grids have COMPLETED and their writes are visible).
+// Every launch goes through launch_k(), which sets cudaLaunchAttributeProgrammaticStreamSerialization; kernels that
+// are not converted must not be launched with it.  Off by default (measured slightly slower under graph replay, see
+// pdl_enabled() in kernels_pointwise.cu); option "pdl" = 1 or FLOWSE_PDL=1 turn it on.
+// ---------------------------------------------------------------------------------------------
+bool& pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  ++launch_counter();
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 constexpr int kGroups = 32;          // GroupNorm groups: min(C/4, 32) == 32 for every C in the net (layerspp.py:219)
 constexpr float kGnEps = 1e-6f;
 constexpr float kSqrt2 = 1.41421356237309504880f;   // np.sqrt(2.) rounded to fp32 (layerspp.py:274)

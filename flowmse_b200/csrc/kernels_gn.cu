@@ -44,6 +44,8 @@ __device__ __forceinline__ uint4 pack8(const uint2 a, const uint2 b) { return ma
 __global__ void __launch_bounds__(256)
 quad_stats_kernel(const float* __restrict__ src, int C, int npix, int chunk, double* __restrict__ qs,
                   double* __restrict__ partials, unsigned* __restrict__ counters) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cvec = C >> 2;                 // quads per pixel
   const int ppi = blockDim.x / cvec;       // pixels per iteration
   const int b = blockIdx.y;
@@ -177,6 +179,8 @@ __device__ __forceinline__ void load_stats(const PrepK& k, int b, float* s_mean,
 // Plain (no resampling): 8 channels per thread, two pixels per loop trip (4 x 16-byte loads in flight).
 __global__ void __launch_bounds__(256)
 gn_prep_plain_kernel(const PrepK k) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = k.C1 + k.C2;
   const int c8 = C >> 3;
   const int ppi = blockDim.x / c8;
@@ -236,6 +240,8 @@ gn_prep_plain_kernel(const PrepK k) {
 // FIR down / up x2 fused with the normalisation (single-source inputs only): 4 channels per thread.
 __global__ void __launch_bounds__(256)
 gn_prep_resample_kernel(const PrepK k) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = k.C1;
   const int cvec = C >> 2;
   const int ppi = blockDim.x / cvec;
@@ -326,8 +332,7 @@ void launch_quad_stats(const float* src, int C, int B, int npix, double* qs, dou
   chunk = ((chunk + ppi - 1) / ppi) * ppi;
   if (chunk < ppi * 4) chunk = ppi * 4;
   dim3 grid((npix + chunk - 1) / chunk, B);
-  quad_stats_kernel<<<grid, 256, 0, s>>>(src, C, npix, chunk, qs, partials, counters);
-  ++launch_counter();
+  launch_k(quad_stats_kernel, grid, dim3(256), 0, s, src, C, npix, chunk, qs, partials, counters);
 }
 
 void launch_gn_prep(const PrepArgs& a, cudaStream_t s) {
@@ -346,9 +351,8 @@ void launch_gn_prep(const PrepArgs& a, cudaStream_t s) {
   const int cap = std::max(1, (148 * 8) / a.B);
   if (blocks > cap) blocks = cap;
   dim3 grid(blocks, a.B);
-  if (a.mode == kPrepPlain) gn_prep_plain_kernel<<<grid, 256, 0, s>>>(k);
-  else gn_prep_resample_kernel<<<grid, 256, 0, s>>>(k);
-  ++launch_counter();
+  if (a.mode == kPrepPlain) launch_k(gn_prep_plain_kernel, grid, dim3(256), 0, s, k);
+  else launch_k(gn_prep_resample_kernel, grid, dim3(256), 0, s, k);
 }
 
 }  // namespace flowse

@@ -2,11 +2,20 @@
 // Each cites the reference line it replaces (paths relative to /root/reference).
 #include "flowse_internal.h"
 
+#include <cstdlib>
+
 namespace flowse {
 
 long long& launch_counter() {
   static long long n = 0;
   return n;
+}
+bool& pdl_enabled() {
+  // Off by default: measured on B200 (bench.py, N=5, B=1, T=512) graph replay is 1.3 % slower with PDL on (26.3 vs
+  // 26.0 ms per sampler call): kernel-to-kernel gaps inside a CUDA graph are already small, and early-scheduled CTAs
+  // of the next kernel compete with the running one.  FLOWSE_PDL=1 / option "pdl" turn it on.
+  static bool on = [] { const char* e = getenv("FLOWSE_PDL"); return e && e[0] == '1'; }();
+  return on;
 }
 
 namespace {
@@ -24,6 +33,8 @@ __device__ __forceinline__ float madd(float a, float b, float c) { return __fadd
 __global__ void __launch_bounds__(256)
 prior_kernel(const float4* __restrict__ y, const float4* __restrict__ z, float sigma, float4* __restrict__ x,
              size_t n4, const float2* y2, const float2* z2, float2* x2, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 a = __ldg(y + i), b = __ldg(z + i);
@@ -40,6 +51,8 @@ prior_kernel(const float4* __restrict__ y, const float4* __restrict__ z, float s
 __global__ void __launch_bounds__(256)
 axpy_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float c, float4* __restrict__ out, size_t n4,
             const float2* a2, const float2* b2, float2* o2, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 u = __ldg(a + i), v = __ldg(b + i);
@@ -55,6 +68,8 @@ axpy_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float c,
 __global__ void __launch_bounds__(256)
 heun_kernel(const float2* __restrict__ x, const float2* __restrict__ v0, const float2* __restrict__ v1, float c,
             float2* __restrict__ out, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float2 a = x[i], p = v0[i], q = v1[i];
@@ -63,6 +78,8 @@ heun_kernel(const float2* __restrict__ x, const float2* __restrict__ v0, const f
 }
 
 __global__ void set_scalars_kernel(float* t_dev, int B, float t, float* step_dev, float step) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) t_dev[i] = t;
   if (i == 0) step_dev[0] = step;
@@ -81,6 +98,8 @@ __global__ void __launch_bounds__(512)
 temb_mlp_kernel(const TembWeights w, const float* __restrict__ t, float* __restrict__ temb_act) {
   __shared__ __align__(16) float emb[256];
   __shared__ __align__(16) float h1[512];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int j = threadIdx.x;
   if (j < 128) {
@@ -125,6 +144,8 @@ temb_mlp_kernel(const TembWeights w, const float* __restrict__ t, float* __restr
 __global__ void __launch_bounds__(256)
 temb_dense_kernel(const float* __restrict__ dw, const float* __restrict__ db, const float* __restrict__ act, int R,
                   int B, float* __restrict__ table) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= R) return;
@@ -157,10 +178,11 @@ conv_in_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const
                double* __restrict__ qstats, int H, int W) {
   __shared__ float4 s_in[6][34];          // 4 channels per pixel, halo 1
   __shared__ float4 s_w[9][4][32];        // [tap][ci][lane] -> 4 consecutive output channels
+  pdl_launch_dependents();
   const int b = blockIdx.z;
   const int h0 = blockIdx.y * 4, w0 = blockIdx.x * 32;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 9 * 4 * 32; i += 256) {
+  for (int i = tid; i < 9 * 4 * 32; i += 256) {      // weights do not depend on the previous kernel
     const int l = i & 31, ci = (i >> 5) & 3, tap = i >> 7;
     float4 v;
     // weight layout [128][4][3][3]
@@ -170,6 +192,7 @@ conv_in_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const
     v.w = wgt[((4 * l + 3) * 4 + ci) * 9 + tap];
     s_w[tap][ci][l] = v;
   }
+  pdl_wait();
   for (int i = tid; i < 6 * 34; i += 256) {
     const int r = i / 34, c = i % 34;
     const int h = h0 + r - 1, w = w0 + c - 1;
@@ -240,6 +263,8 @@ conv_in_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 fir_down4_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   // in: [B][2H][2W], out: [B][H][W]
   const size_t total = static_cast<size_t>(B) * H * W;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -272,6 +297,8 @@ fir_down4_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B,
 __global__ void __launch_bounds__(256)
 combine_kernel(const float* __restrict__ h, const float4* __restrict__ pyr, const float* __restrict__ w,
                const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ qstats, int npix, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cvec = C >> 2;
   const int ppi = blockDim.x / cvec;
   const int b = blockIdx.y;
@@ -316,6 +343,8 @@ combine_kernel(const float* __restrict__ h, const float4* __restrict__ pyr, cons
 __global__ void __launch_bounds__(256)
 pyr_accum_kernel(const float4* __restrict__ prev, const float4* __restrict__ head, float4* __restrict__ out, int B,
                  int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = static_cast<size_t>(B) * H * W;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -355,6 +384,8 @@ __global__ void __launch_bounds__(256)
 final_kernel(const float4* __restrict__ pyr, const float* __restrict__ t, const float* __restrict__ wo,
              const float* __restrict__ bo, const float2* __restrict__ xin, const float* __restrict__ step_dev,
              float2* __restrict__ out, int mode, int B, int HW) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = static_cast<size_t>(B) * HW;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   const float w00 = wo[0], w01 = wo[1], w02 = wo[2], w03 = wo[3];
@@ -379,6 +410,8 @@ final_kernel(const float4* __restrict__ pyr, const float* __restrict__ t, const 
 // row softmax, one warp per row                        (layerspp.py:84)
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(float* __restrict__ s, int rows, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -397,22 +430,19 @@ softmax_rows_kernel(float* __restrict__ s, int rows, int cols) {
 }  // namespace
 
 void launch_set_scalars(float* t_dev, int B, float t, float* step_dev, float step, cudaStream_t s) {
-  set_scalars_kernel<<<(B + 127) / 128, 128, 0, s>>>(t_dev, B, t, step_dev, step);
-  ++launch_counter();
+  launch_k(set_scalars_kernel, dim3((B + 127) / 128), dim3(128), 0, s, t_dev, B, t, step_dev, step);
 }
 
 void launch_prior(const float2* y, const float2* z, float sigma, float2* x, size_t n, cudaStream_t s) {
   const size_t n4 = n / 2;
-  prior_kernel<<<grid_for(n4), 256, 0, s>>>(reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(z),
-                                            sigma, reinterpret_cast<float4*>(x), n4, y, z, x, n);
-  ++launch_counter();
+  launch_k(prior_kernel, dim3(grid_for(n4)), dim3(256), 0, s, reinterpret_cast<const float4*>(y),
+           reinterpret_cast<const float4*>(z), sigma, reinterpret_cast<float4*>(x), n4, y, z, x, n);
 }
 
 void launch_axpy_c(const float2* a, const float2* b, float c, float2* out, size_t n, cudaStream_t s) {
   const size_t n4 = n / 2;
-  axpy_kernel<<<grid_for(n4), 256, 0, s>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), c,
-                                           reinterpret_cast<float4*>(out), n4, a, b, out, n);
-  ++launch_counter();
+  launch_k(axpy_kernel, dim3(grid_for(n4)), dim3(256), 0, s, reinterpret_cast<const float4*>(a),
+           reinterpret_cast<const float4*>(b), c, reinterpret_cast<float4*>(out), n4, a, b, out, n);
 }
 
 void launch_euler_update(const float2* x, const float2* v, float dt, float2* out, size_t n, cudaStream_t s) {
@@ -421,30 +451,25 @@ void launch_euler_update(const float2* x, const float2* v, float dt, float2* out
 
 void launch_heun_combine(const float2* x, const float2* v0, const float2* v1, float c, float2* out, size_t n,
                          cudaStream_t s) {
-  heun_kernel<<<grid_for(n), 256, 0, s>>>(x, v0, v1, c, out, n);
-  ++launch_counter();
+  launch_k(heun_kernel, dim3(grid_for(n)), dim3(256), 0, s, x, v0, v1, c, out, n);
 }
 
 void launch_temb(const TembWeights& w, const float* t, int B, float* temb_act, float* bias_table, cudaStream_t s) {
-  temb_mlp_kernel<<<B, 512, 0, s>>>(w, t, temb_act);
-  ++launch_counter();
+  launch_k(temb_mlp_kernel, dim3(B), dim3(512), 0, s, w, t, temb_act);
   const int warps_per_block = 8;
-  temb_dense_kernel<<<(w.R + warps_per_block - 1) / warps_per_block, 256, 0, s>>>(w.dense_w, w.dense_b, temb_act, w.R,
-                                                                                  B, bias_table);
-  ++launch_counter();
+  launch_k(temb_dense_kernel, dim3((w.R + warps_per_block - 1) / warps_per_block), dim3(256), 0, s, w.dense_w, w.dense_b,
+           static_cast<const float*>(temb_act), w.R, B, bias_table);
 }
 
 void launch_conv_in(const float2* x, const float2* y, const float* w, const float* bias, float* out, float4* pyr,
                     double* qstats, int B, int H, int W, cudaStream_t s) {
   dim3 grid((W + 31) / 32, (H + 3) / 4, B);
-  conv_in_kernel<<<grid, 256, 0, s>>>(x, y, w, bias, out, pyr, qstats, H, W);
-  ++launch_counter();
+  launch_k(conv_in_kernel, grid, dim3(256), 0, s, x, y, w, bias, out, pyr, qstats, H, W);
 }
 
 void launch_fir_down4(const float4* in, float4* out, int B, int H, int W, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * H * W;
-  fir_down4_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out, B, H, W);
-  ++launch_counter();
+  launch_k(fir_down4_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, in, out, B, H, W);
 }
 
 void launch_combine(const float* h, const float4* pyr, const float* w, const float* b, float* out, double* qstats,
@@ -455,26 +480,22 @@ void launch_combine(const float* h, const float4* pyr, const float* w, const flo
   const int cap = std::max(1, (148 * 8) / B);
   if (blocks > cap) blocks = cap;
   dim3 grid(blocks, B);
-  combine_kernel<<<grid, 256, 0, s>>>(h, pyr, w, b, out, qstats, npix, C);
-  ++launch_counter();
+  launch_k(combine_kernel, grid, dim3(256), 0, s, h, pyr, w, b, out, qstats, npix, C);
 }
 
 void launch_pyr_accum(const float4* prev, const float4* head, float4* out, int B, int H, int W, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * H * W;
-  pyr_accum_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(prev, head, out, B, H, W);
-  ++launch_counter();
+  launch_k(pyr_accum_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, prev, head, out, B, H, W);
 }
 
 void launch_final(const float4* pyr, const float* t, const float* wo, const float* bo, const float2* xin,
                   const float* stepsize_dev, float2* out, int mode, int B, int HW, cudaStream_t s) {
-  final_kernel<<<grid_for(static_cast<size_t>(B) * HW), 256, 0, s>>>(pyr, t, wo, bo, xin, stepsize_dev, out, mode, B,
-                                                                      HW);
-  ++launch_counter();
+  launch_k(final_kernel, dim3(grid_for(static_cast<size_t>(B) * HW)), dim3(256), 0, s, pyr, t, wo, bo, xin, stepsize_dev,
+           out, mode, B, HW);
 }
 
 void launch_softmax_rows(float* sm, int rows, int cols, cudaStream_t st) {
-  softmax_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(sm, rows, cols);
-  ++launch_counter();
+  launch_k(softmax_rows_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, sm, rows, cols);
 }
 
 }  // namespace flowse

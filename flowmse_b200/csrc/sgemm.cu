@@ -23,6 +23,8 @@ sgemm_kernel(const SgemmArgs a) {
   constexpr int B_F4 = TN * TK / 4 / 256;             // 2
   __shared__ __align__(16) float sA[TK][TM + LDS_PAD];
   __shared__ __align__(16) float sB[TK][TN + LDS_PAD];
+  pdl_launch_dependents();
+  pdl_wait();
   const int bz = blockIdx.z;
   const float* __restrict__ A = a.A + bz * a.strideA;
   const float* __restrict__ Bm = a.Bm + bz * a.strideB;
@@ -170,12 +172,11 @@ void launch_sgemm(const SgemmArgs& a, cudaStream_t s) {
   const long long tiles64 = static_cast<long long>((a.N + TN - 1) / TN) * ((a.M + 63) / 64) * a.batch;
   if (tiles64 >= 120 && a.M > 32) {
     dim3 grid((a.N + TN - 1) / TN, (a.M + 63) / 64, a.batch);
-    sgemm_kernel<64><<<grid, 256, 0, s>>>(a);
+    launch_k(sgemm_kernel<64>, grid, dim3(256), 0, s, a);
   } else {
     dim3 grid((a.N + TN - 1) / TN, (a.M + 31) / 32, a.batch);
-    sgemm_kernel<32><<<grid, 256, 0, s>>>(a);
+    launch_k(sgemm_kernel<32>, grid, dim3(256), 0, s, a);
   }
-  ++launch_counter();
 }
 
 }  // namespace flowse

@@ -77,7 +77,8 @@ int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const voi
 
 /* Options: "conv_impl" 0 = tcgen05 (default: halo kernel on high-resolution layers, per-tap kernel otherwise),
  * 1 = SIMT cross-check, 2 = per-tap kernel everywhere, 3 = like 0 with 3 rotating main accumulators in the halo kernel,
- * 4 = like 0 with the CTA-pair (cta_group::2) halo kernel; "graph" 0/1 = replay each NFE as a CUDA graph. */
+ * 4 = like 0 with the CTA-pair (cta_group::2) halo kernel; "graph" 0/1 = replay each NFE as a CUDA graph; "pdl" 0/1 = programmatic dependent launch between kernels
+ * (process-wide, default 0: measured slower under graph replay). */
 int flowse_set_option(flowse_ctx* ctx, const char* key, int value);
 
 /* Number of this library's kernel launches (graph kernel nodes included) since the context was created. */
