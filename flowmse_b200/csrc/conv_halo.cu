@@ -31,6 +31,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
+#include <cstdlib>
 
 namespace flowse {
 
@@ -57,7 +59,14 @@ struct HCfg {
   static constexpr int B_PLANE = B_ROWS * 128;
   static constexpr int B_STAGE_BYTES = 2 * B_PLANE;
   static constexpr int B_STAGES = (BN >= 128) ? (PAIR ? 6 : 3) : 8;
-  static constexpr int SLOT_COLS = (BN < 32) ? 32 : BN;
+  // FUSED (one main accumulator, single CTA): the hi and lo weight planes of a stage are contiguous in shared memory, so
+  // A_hi x [B_hi ; B_lo]^T is ONE MMA of N = 2*BN whose accumulator is [main | correction]; A_lo x B_hi^T follows with
+  // N = BN into the correction columns.  A_hi is fetched from shared memory once instead of twice: 20 KB instead of
+  // 24 KB of operand reads per K step.  The measured limiter of this kernel is exactly that: the issuer thread never
+  // waits for data, but a 128x128x16 MMA retires every ~80 cycles instead of 64 because its 8 KB of operands plus the
+  // TMA writes exceed the 128 B/cycle of the shared-memory port (tools/dbg_halo.py, profiles/README.md).
+  static constexpr bool FUSED = (NMAIN == 1) && !PAIR;
+  static constexpr int SLOT_COLS = FUSED ? BN : ((BN < 32) ? 32 : BN);
   static constexpr int NSLOT = NMAIN + 1;                          // hi*hi chains + one correction accumulator
   static constexpr int NBUF = (NSLOT * SLOT_COLS * 2 <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS_RAW = NBUF * NSLOT * SLOT_COLS;
@@ -81,6 +90,7 @@ struct HaloParams {
   float* out;
   int div_sqrt2;
   double* qstats;
+  long long* dbg;   // optional per-CTA wait-cycle counters (FLOWSE_CONV_DBG=1): 8 per CTA
 };
 
 struct TileCoord { int b, h0, w0, n0; };
@@ -226,11 +236,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
+      long long w_pa = 0, w_pb = 0;            // cycles the producer waited for a free A / B stage
       // PAIR: the full barriers that count are the leader's; this CTA's loads complete there
       auto full_addr = [&](uint32_t local) { return PAIR ? map_to_cta(local, 0) : local; };
       auto issue_A = [&](int item, int c) {
         const TileCoord t = decode_tile<BN, PAIR>(p, item, rank);
-        ptx::mbar_wait(a_empty(as), aph ^ 1u);
+        { const long long c0 = clock64(); ptx::mbar_wait(a_empty(as), aph ^ 1u); w_pa += clock64() - c0; }
         if (rank == 0) ptx::mbar_expect_tx(a_full(as), 2 * A_PLANE_BYTES * kCtas);
         const bool main = c < p.nchunk_main;
         const CUtensorMap* m = main ? &tmA : &tmX;
@@ -256,7 +267,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int pre = ntap > 2 ? 2 : ntap - 1;       // prefetch the next halo while this chunk's taps stream
           for (int tp = 0; tp < ntap; ++tp) {
             const int kb = main ? tp * p.nchunk_main + c : 9 * p.nchunk_main + (c - p.nchunk_main);
-            ptx::mbar_wait(b_empty(bs), bph ^ 1u);
+            { const long long c0 = clock64(); ptx::mbar_wait(b_empty(bs), bph ^ 1u); w_pb += clock64() - c0; }
             if (rank == 0) ptx::mbar_expect_tx(b_full(bs), C::B_STAGE_BYTES * kCtas);
             const uint32_t bar = full_addr(b_full(bs));
             if constexpr (PAIR) {
@@ -274,6 +285,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      if (p.dbg) { p.dbg[blockIdx.x * 8 + 4] = w_pa; p.dbg[blockIdx.x * 8 + 5] = w_pb; }
       if constexpr (PAIR) {
         // drain: every multicast commit aimed at this CTA's empty barriers has landed before the CTA may exit
         for (int i = 0; i < C::B_STAGES; ++i) {
@@ -301,10 +313,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int it = 0;
+      long long w_t = 0, w_a = 0, w_b = 0;     // cycles the issuer waited for TMEM / A halo / B block
+      const long long t_begin = clock64();
       for (int item = item0; item < p.num_items; item += item_stride, ++it) {
         const int buf = it % C::NBUF;
         const uint32_t use = static_cast<uint32_t>(it / C::NBUF);
-        ptx::mbar_wait(t_empty(buf), (use & 1u) ^ 1u);        // epilogue has drained this accumulator buffer
+        { const long long c0 = clock64(); ptx::mbar_wait(t_empty(buf), (use & 1u) ^ 1u); w_t += clock64() - c0; }   // epilogue has drained this accumulator buffer
         ptx::tc_fence_after();
         const uint32_t acc = tmem_acc + static_cast<uint32_t>(buf * C::NSLOT * C::SLOT_COLS);
         const uint32_t d_corr = acc + static_cast<uint32_t>(NMAIN * C::SLOT_COLS);
@@ -312,9 +326,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = 0; c < nchunks; ++c) {
           const bool main = c < p.nchunk_main;
           const int ntap = main ? 9 : 1;
-          ptx::mbar_wait(a_full(as), aph);
+          { const long long c0 = clock64(); ptx::mbar_wait(a_full(as), aph); w_a += clock64() - c0; }
           for (int tp = 0; tp < ntap; ++tp) {
-            ptx::mbar_wait(b_full(bs), bph);
+            { const long long c0 = clock64(); ptx::mbar_wait(b_full(bs), bph); w_b += clock64() - c0; }
             ptx::tc_fence_after();
             // view of the halo for this tap: rows shifted by (dy+1) halo rows and (dx+1) pixels
             const int shift = main ? (tp / 3) * HALO_W + (tp % 3) : HALO_W + 1;
@@ -329,10 +343,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint64_t dA_lo = make_desc_sw128(a_lo + koff, A_SBO);
               const uint64_t dB_hi = make_desc_sw128(b_hi + koff, 1024);
               const uint64_t dB_lo = make_desc_sw128(b_lo + koff, 1024);
-              const uint32_t d_main = acc + static_cast<uint32_t>((ks % NMAIN) * C::SLOT_COLS);
-              mma(d_main, dA_hi, dB_hi, ks >= NMAIN ? 1u : 0u);
-              mma(d_corr, dA_hi, dB_lo, ks > 0 ? 1u : 0u);
-              mma(d_corr, dA_lo, dB_hi, 1u);
+              if constexpr (C::FUSED) {
+                constexpr uint32_t idesc2 = ptx::make_idesc_f16(BM, 2 * BN);
+                ptx::mma_f16_ss(acc, dA_hi, dB_hi, idesc2, ks > 0 ? 1u : 0u);     // [main | corr] += A_hi x [B_hi ; B_lo]^T
+                ptx::mma_f16_ss(d_corr, dA_lo, dB_hi, idesc, 1u);                 // corr += A_lo x B_hi^T
+              } else {
+                const uint32_t d_main = acc + static_cast<uint32_t>((ks % NMAIN) * C::SLOT_COLS);
+                mma(d_main, dA_hi, dB_hi, ks >= NMAIN ? 1u : 0u);
+                mma(d_corr, dA_hi, dB_lo, ks > 0 ? 1u : 0u);
+                mma(d_corr, dA_lo, dB_hi, 1u);
+              }
             }
             commit(b_empty(bs));
             if (++bs == C::B_STAGES) { bs = 0; bph ^= 1u; }
@@ -341,6 +361,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (++as == A_STAGES) { as = 0; aph ^= 1u; }
         }
         commit(t_full(buf));
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 1] = w_t;
+        p.dbg[blockIdx.x * 8 + 2] = w_a; p.dbg[blockIdx.x * 8 + 3] = w_b;
       }
     }
   } else if (warp >= kFirstEpiWarp) {
@@ -617,8 +641,28 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   } else {
     cfg.gridDim = dim3(std::min(p.num_items, num_sms()));
   }
+  static const bool dbg = getenv("FLOWSE_CONV_DBG") != nullptr;
+  long long* dbuf = nullptr;
+  const size_t nctas = cfg.gridDim.x;
+  if (dbg) { cudaMalloc(&dbuf, nctas * 8 * sizeof(long long)); cudaMemset(dbuf, 0, nctas * 8 * sizeof(long long)); p.dbg = dbuf; }
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, NMAIN, PAIR>, tmA, tmX, tmW, p);
   ++launch_counter();
+  if (dbg) {
+    cudaStreamSynchronize(s);
+    std::vector<long long> h(nctas * 8);
+    cudaMemcpy(h.data(), dbuf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dbuf);
+    double sum[8] = {0}; int nl = 0;
+    for (size_t c = 0; c < nctas; ++c) {
+      if (h[c * 8] > 0) ++nl;
+      for (int k = 0; k < 8; ++k) sum[k] += static_cast<double>(h[c * 8 + k]);
+    }
+    if (nl == 0) nl = 1;
+    const double kb_per_cta = static_cast<double>(p.num_items) * (9.0 * p.nchunk_main + p.nchunk_sc) / nl;
+    fprintf(stderr, "[halo dbg] items=%d issuing ctas=%d kblocks/cta=%.0f (mma floor %.0f cyc) | issuer loop %.0f cyc: wait tmem %.0f, A %.0f, B %.0f | producer wait: A-free %.0f, B-free %.0f\n",
+            p.num_items, nl, kb_per_cta, kb_per_cta * 768.0 * (BN / 128.0), sum[0] / nl, sum[1] / nl, sum[2] / nl, sum[3] / nl,
+            sum[4] / nctas, sum[5] / nctas);
+  }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv_halo launch: ") + cudaGetErrorString(e); return 1; }
   return 0;
