@@ -263,16 +263,41 @@ def run_ours(args):
             k = by_kind.setdefault(o["kind"], dict(ms=0.0, n=0, flops=0.0))
             k["ms"] += o["ms"]; k["n"] += 1; k["flops"] += o["flops"]
         conv = by_kind["conv_gemm"]
-        achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
+        # dominant kernel = conv_halo_kernel<128,1,0>: the 3x3 convs of the three highest resolutions (same eligibility
+        # rule as engine.cu run_conv); the low-resolution / pyramid-head launches use other instantiations
+        def is_halo(o):
+            return (o["kind"] == "conv_gemm" and o["Cout"] >= 128 and o["H"] % 16 == 0 and o["W"] % 8 == 0 and
+                    B * (o["H"] // 16) * (o["W"] // 8) * ((o["Cout"] + 127) // 128) >= 100)
+        halo = [o for o in ops if is_halo(o)]
+        ncu_traffic = {}
+        try:    # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture
+            summ = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_full_summary.json")))
+            for name, rec in summ.items():
+                if name.startswith("conv_halo_kernel<128,1,0>"):
+                    ncu_traffic = {"bytes": rec["dram_bytes_read"] + rec["dram_bytes_write"],
+                                   "note": f"dram__bytes_read.sum + dram__bytes_write.sum of ONE launch ({rec['shape']}; "
+                                           f"algorithmic 201.3 MB: 128 MiB hi/lo activations + 64 MiB fp32 output + "
+                                           f"1.2 MB weights) from profiles/r1_conv_halo_full.ncu-rep"}
+        except Exception:
+            pass
+        h_ms = sum(o["ms"] for o in halo); h_fl = sum(o["flops"] for o in halo)
+        achieved = h_fl / (h_ms * 1e-3) / 1e12
+        all_conv = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
         result["roofline"] = {
-            "bound": "tensor", "kernel": "conv_gemm_tcgen05_kernel (all ResBlock / pyramid-head convolutions)",
+            "bound": "tensor", "kernel": "conv_halo_kernel<128,1,0> (3x3 ResBlock convolutions at 256xT, 128xT/2, 64xT/4)",
             "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
-            "traffic": None,
+            "traffic": ncu_traffic.get("bytes"), "traffic_note": ncu_traffic.get("note"),
+            "frac_of_burst_peak": achieved / peaks["tf_burst"],
             "issued_mma_tflops": 3 * achieved, "issued_frac": 3 * achieved / peaks["tf_sustained"],
-            "avg_launch_ms": conv["ms"] / conv["n"], "launches_per_nfe": conv["n"],
-            "algorithmic_gflop_per_nfe": conv["flops"] / 1e9, "share_of_nfe_time": conv["ms"] / tot_ms,
-            "peak_source": peaks["source"] + " bf16 dense sustained (fp16 issues at the same rate)",
+            "issued_frac_of_burst_peak": 3 * achieved / peaks["tf_burst"],
+            "avg_launch_ms": h_ms / max(1, len(halo)), "launches_per_nfe": len(halo),
+            "algorithmic_gflop_per_launch_avg": h_fl / max(1, len(halo)) / 1e9,
+            "share_of_nfe_time": h_ms / tot_ms,
+            "peak_source": peaks["source"] + " bf16 dense sustained (the kernel is timed inside a step; fp16 issues at the "
+                           "same rate); parity costs 3 issued MMAs per algorithmic product, so frac <= 1/3",
             "how": "CUDA events after every op of one NFE on a private stream (flowse_profile_forward), after the timed region",
+            "all_conv_launches": {"launches_per_nfe": conv["n"], "achieved": all_conv, "frac": all_conv / peaks["tf_sustained"],
+                                  "algorithmic_gflop_per_nfe": conv["flops"] / 1e9, "share_of_nfe_time": conv["ms"] / tot_ms},
             "nfe_ms_by_kernel_family": {k: round(v["ms"], 4) for k, v in by_kind.items()},
         }
         # Euler-update kernel against the HBM roofline, on a buffer larger than L2 (B=1 moves only 3 MiB per launch)
