@@ -189,3 +189,26 @@ def test_enhance_sharded_gloo_world2():
         loads = dict(ret)
     assert sorted(loads) == [0, 1]
     assert abs(loads[0] - loads[1]) <= 128                 # LPT balance on [128,64,192,64,128,256,64]
+
+
+def test_config1_stft_plumbing_matches_reference_golden(golden_dir):
+    """BASELINE.json configs[0]: 4 s synthetic wav -> STFT (n_fft 510, hop 128, hann) -> |X|^0.5 e^{j arg X} * 0.15 ->
+    pad_spec, against values produced by the reference's own _stft/_forward_transform/pad_spec (oracle/gen_golden.py)."""
+    from flowmse_b200.model import SpecTransform
+    from flowmse_b200.util.other import pad_spec
+    g = np.load(os.path.join(golden_dir, "stft_cfg1.npz"))
+    torch.manual_seed(0)
+    n = 64000
+    tgrid = torch.arange(n) / 16000.0
+    wav = 0.1 * torch.randn(1, n) + 0.5 * torch.sin(2 * np.pi * 220 * tgrid) + 0.25 * torch.sin(2 * np.pi * 1320 * tgrid)
+    wav = wav / wav.abs().max()
+    assert np.array_equal(wav.numpy()[:, :4096], g["wav"])           # same synthetic input as the generator script
+    st = SpecTransform()
+    Y = torch.unsqueeze(st.spec_fwd(st.stft(wav)), 0)
+    assert list(Y.shape) == list(g["shape"]) == [1, 1, 256, 501]
+    Yp = pad_spec(Y)
+    assert list(Yp.shape) == list(g["padded_shape"]) == [1, 1, 256, 512]
+    assert torch.allclose(torch.view_as_real(Yp[0, 0, :, :8]), torch.from_numpy(g["Y_head"]), rtol=1e-5, atol=1e-6)
+    # round trip of the transform pair and of the STFT pair (to_audio path, model.py:190-203)
+    back = st.istft(st.spec_back(st.spec_fwd(st.stft(wav))), length=n)
+    assert torch.allclose(back, wav, atol=2e-4)
