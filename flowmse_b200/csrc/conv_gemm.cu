@@ -78,6 +78,10 @@ struct GemmParams {
   int ksplit;
   float* partial;
   long long partial_plane;   // elements per split = B*H*W*ldc
+  // In-kernel reduction (counters != null): the ksplit CTAs of an output tile (co-resident: cooperative launch, grid
+  // <= #SMs) meet at a counter once their partial tiles are in L2, then CTA z sums rows [z*128/S, (z+1)*128/S) of all
+  // partials in fixed z order and applies the epilogue - no second kernel, same deterministic summation order.
+  unsigned* counters;        // [tiles][2] {arrived, departed}, zero between launches
 };
 
 template <int BN>
@@ -329,6 +333,77 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   }
 
+  if (p.counters && warp >= 2) {
+    // ---------------------------------------------------------------- in-kernel split-K reduction (epilogue warps)
+    __shared__ float s_red[kEpiWarps][32][2];
+    const int etid = threadIdx.x - 64;
+    const int S = p.ksplit;
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    unsigned* cnt = p.counters + 2 * tile;
+    __threadfence();                                       // this thread's partial stores are visible device-wide
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (etid == 0) {
+      atomicAdd(cnt, 1u);
+      unsigned v = 0;
+      unsigned long long t0 = 0;
+      for (unsigned it = 0;; ++it) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+        if (v >= static_cast<unsigned>(S)) break;
+        if ((it & 0xff) == 0xff) {                        // bounded: a scheduling problem traps instead of hanging
+          const unsigned long long now = ptx::globaltimer_ns();
+          if (t0 == 0) t0 = now; else if (now - t0 > 4000000000ull) __trap();
+        }
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    __threadfence();
+    const int z = blockIdx.z;
+    const int r_lo = (z * BM) / S, r_hi = ((z + 1) * BM) / S;
+    const int ncol4 = min(BN, p.Cout - n0) >> 2;           // float4 columns of this tile
+    const int c4 = etid & 31, rg = etid >> 5;              // fixed column quad per thread, 8 row groups
+    const float postf = p.div_sqrt2 ? 0.70710678118654752440f : 1.0f;
+    float qs_s = 0.f, qs_q = 0.f;
+    if (c4 < ncol4) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(b) * p.bias_bstride + n0) + c4);
+      for (int r = r_lo + rg; r < r_hi; r += kEpiWarps) {
+        const int th = r / p.TW, tw = r - th * p.TW;
+        const int h = h0 + th, w = w0 + tw;
+        if (h >= p.H || w >= p.W) continue;
+        const long long o = static_cast<long long>((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.ldc + n0 + 4 * c4;
+        float4 acc = __ldcg(reinterpret_cast<const float4*>(p.partial + o));
+        for (int zz = 1; zz < S; ++zz) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(p.partial + zz * p.partial_plane + o));
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.residual) rr = __ldg(reinterpret_cast<const float4*>(p.residual + o));
+        float4 v;
+        v.x = (acc.x + bv.x + rr.x) * postf; v.y = (acc.y + bv.y + rr.y) * postf;
+        v.z = (acc.z + bv.z + rr.z) * postf; v.w = (acc.w + bv.w + rr.w) * postf;
+        *reinterpret_cast<float4*>(p.out + o) = v;
+        qs_s += (v.x + v.y) + (v.z + v.w);
+        qs_q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+    }
+    if (p.qstats) {
+      s_red[rg][c4][0] = qs_s; s_red[rg][c4][1] = qs_q;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (etid < ncol4) {
+        float as = 0.f, aq = 0.f;
+#pragma unroll
+        for (int g = 0; g < kEpiWarps; ++g) { as += s_red[g][etid][0]; aq += s_red[g][etid][1]; }
+        double* dst = qstat_slot(p.qstats, b, tile * S + z, p.Cout >> 2) + static_cast<size_t>((n0 >> 2) + etid) * 2;
+        atomicAdd(dst, static_cast<double>(as));
+        atomicAdd(dst + 1, static_cast<double>(aq));
+      }
+    }
+    // every CTA of the tile has read what it needs once all S have departed: the last one re-arms the counters
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (etid == 0) {
+      if (atomicAdd(cnt + 1, 1u) == static_cast<unsigned>(S - 1)) { cnt[0] = 0u; cnt[1] = 0u; __threadfence(); }
+    }
+  }
+
   if (threadIdx.x == 64) stamp(4);
   ptx::tc_fence_before();
   __syncthreads();
@@ -501,6 +576,17 @@ bool make_w_map(CUtensorMap* m, const __half* base, int Npad, int K, int BN, std
   return true;
 }
 
+int num_sms_gemm() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 void choose_tile(int H, int W, int& TW, int& TH) {
   long best = LONG_MAX;
   TW = 128; TH = 1;
@@ -527,7 +613,7 @@ GemmParams make_params(const ConvGemmArgs& a) {
   p.out = a.out;
   p.div_sqrt2 = a.div_sqrt2;
   p.dbg = nullptr;
-  p.ksplit = 1; p.partial = nullptr; p.partial_plane = 0;
+  p.ksplit = 1; p.partial = nullptr; p.partial_plane = 0; p.counters = nullptr;
   p.qstats = a.qstats;
   return p;
 }
@@ -573,11 +659,32 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
     if (S < 2) S = 1;
     if (S > 1) { p.ksplit = S; p.partial = a.splitk_scratch; p.partial_plane = plane; grid.z = S; }
   }
+  // All CTAs fit in one co-resident wave (one CTA per SM), so the reduction CAN run inside the kernel.  Measured on B200
+  // (bench.py, B=1, T=512) it is slower than the separate reduce kernel: 23.83 vs 23.26 ms per sampler call - under
+  // graph replay a kernel boundary costs less than the tile-wide counter wait plus a 256-thread slice reduction.
+  // Opt-in (FLOWSE_SPLITK_FUSED=1) for experiments; the default is the two-pass path.
+  static const bool want_fused = getenv("FLOWSE_SPLITK_FUSED") != nullptr;
+  const bool fused_reduce = want_fused && S > 1 && a.splitk_counters && tiles * S <= num_sms_gemm() &&
+                            tiles <= kSplitKCounterTiles;
+  if (fused_reduce) p.counters = a.splitk_counters;
   static const bool dbg = getenv("FLOWSE_CONV_DBG") != nullptr;
   long long* dbuf = nullptr;
   const size_t ncta = static_cast<size_t>(grid.x) * grid.y;
   if (dbg) { cudaMalloc(&dbuf, ncta * 8 * sizeof(long long)); cudaMemset(dbuf, 0, ncta * 8 * sizeof(long long)); p.dbg = dbuf; }
-  launch_k(conv_gemm_tcgen05_kernel<BN>, grid, dim3(NUM_THREADS), C::SMEM_BYTES, s, tmA, tmX, tmW, p);
+  if (fused_reduce) {
+    // cooperative: the runtime guarantees (or refuses) co-residency of the whole grid, which the counter wait needs
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ++launch_counter();
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN>, tmA, tmX, tmW, p);
+    if (le != cudaSuccess) { if (err) *err = std::string("conv_gemm cooperative launch: ") + cudaGetErrorString(le); return 1; }
+  } else {
+    launch_k(conv_gemm_tcgen05_kernel<BN>, grid, dim3(NUM_THREADS), C::SMEM_BYTES, s, tmA, tmX, tmW, p);
+  }
   if (dbg) {
     cudaStreamSynchronize(s);
     std::vector<long long> h(ncta * 8);
@@ -593,7 +700,7 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
             ncta, p.ntaps * p.nchunk_main + p.nchunk_sc, ph[0] / ncta / 1e3, ph[1] / ncta / 1e3, ph[2] / ncta / 1e3,
             ph[3] / ncta / 1e3, ph[4] / ncta / 1e3, (tmax - tmin) / 1e3);
   }
-  if (S > 1) {
+  if (S > 1 && !fused_reduce) {
     const int n4b = a.H * a.W * a.ldc / 4;
     const bool can_stats = a.qstats && (256 % (a.ldc / 4) == 0);
     dim3 rgrid((n4b + 255) / 256, a.B);

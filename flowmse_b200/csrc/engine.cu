@@ -348,6 +348,7 @@ struct Builder {
   __half *scrA = nullptr, *scrX = nullptr;
   float *scrH1 = nullptr, *scrF = nullptr, *scrQKV = nullptr, *scrS = nullptr, *scrO = nullptr, *scrHead = nullptr;
   float *temb_act = nullptr, *bias_table = nullptr, *splitk = nullptr;
+  unsigned* splitk_cnt = nullptr;
 
   void push(int nk, std::function<int(cudaStream_t)> fn, int kind = 0, double flops = 0.0, int i0 = 0, int i1 = 0,
             int i2 = 0, int i3 = 0) {
@@ -391,7 +392,7 @@ struct Builder {
     c0.wscale_inv = r.conv0.wscale_inv; c0.bias = bias_table + r.dense_off; c0.bias_bstride = ctx->dense_rows;
     c0.residual = nullptr; c0.div_sqrt2 = 0; c0.out = scrH1; c0.Cout = r.cout; c0.ldc = r.cout;
     c0.B = B; c0.H = Ho; c0.W = Wo;
-    c0.splitk_scratch = splitk; c0.splitk_scratch_elems = kSplitKScratchElems; c0.qstats = st1;
+    c0.splitk_scratch = splitk; c0.splitk_scratch_elems = kSplitKScratchElems; c0.splitk_counters = splitk_cnt; c0.qstats = st1;
     { flowse_ctx* cx = ctx; push(2, [=](cudaStream_t s) { return run_conv(cx, c0, s); }, 3, conv_flops(c0), c0.H, c0.W, c0.ntaps * c0.Cin + (c0.X ? c0.Cin2 : 0), c0.Cout); }
     float* h1 = scrH1; const int Co = r.cout;
     PrepArgs pb{};
@@ -403,7 +404,7 @@ struct Builder {
     c1.Wp = r.conv1.wp; c1.Npad = r.conv1.Npad; c1.wscale_inv = r.conv1.wscale_inv; c1.bias = r.bias1;
     c1.bias_bstride = 0; c1.residual = r.has_sc ? nullptr : s1; c1.div_sqrt2 = 1; c1.out = out.p; c1.Cout = Co;
     c1.ldc = Co; c1.B = B; c1.H = Ho; c1.W = Wo;
-    c1.splitk_scratch = splitk; c1.splitk_scratch_elems = kSplitKScratchElems; c1.qstats = out.qs;
+    c1.splitk_scratch = splitk; c1.splitk_scratch_elems = kSplitKScratchElems; c1.splitk_counters = splitk_cnt; c1.qstats = out.qs;
     { flowse_ctx* cx = ctx; push(2, [=](cudaStream_t s) { return run_conv(cx, c1, s); }, 3, conv_flops(c1), c1.H, c1.W, c1.ntaps * c1.Cin + (c1.X ? c1.Cin2 : 0), c1.Cout); }
     plan->taps[mi] = out;
     return out;
@@ -469,6 +470,7 @@ struct Builder {
     scrO = ar.alloc<float>(static_cast<size_t>(B) * La * 256);
     scrHead = ar.alloc<float>(top * 4);
     splitk = ar.alloc<float>(kSplitKScratchElems);
+    splitk_cnt = ar.alloc<unsigned>(2 * kSplitKCounterTiles);      // arena is zero-initialised; the kernel re-arms them
     plan->stats_bytes = static_cast<size_t>(kMaxStatSlots) * B * kStatSlotDoubles * sizeof(double);
     plan->stats = ar.alloc<double>(plan->stats_bytes / sizeof(double));
     plan->gn_partials = ar.alloc<double>(static_cast<size_t>(B) * gn_stats_max_blocks() * 256);
@@ -537,7 +539,7 @@ struct Builder {
         ConvGemmArgs c{};
         c.A = scrA; c.Cin = C; c.ntaps = 9; c.Wp = hw.conv.wp; c.Npad = hw.conv.Npad; c.wscale_inv = hw.conv.wscale_inv;
         c.bias = hw.bias; c.bias_bstride = 0; c.out = scrHead; c.Cout = 4; c.ldc = 4; c.B = B; c.H = Hh; c.W = Ww;
-        c.splitk_scratch = splitk; c.splitk_scratch_elems = kSplitKScratchElems;
+        c.splitk_scratch = splitk; c.splitk_scratch_elems = kSplitKScratchElems; c.splitk_counters = splitk_cnt;
         { flowse_ctx* cx = ctx; push(2, [=](cudaStream_t s) { return run_conv(cx, c, s); }, 3, conv_flops(c), c.H, c.W, c.ntaps * c.Cin + (c.X ? c.Cin2 : 0), c.Cout); }
         float4* pyr = ar.alloc<float4>(static_cast<size_t>(B) * Hh * Ww);
         const float4* prev = pyr_prev; const float4* head = reinterpret_cast<const float4*>(scrHead);
@@ -929,8 +931,12 @@ int flowse_op_conv_gemm(flowse_ctx* ctx, const void* A, int Cin, int ntaps, cons
   a.Wp = static_cast<const __half*>(Wp); a.Npad = Npad; a.wscale_inv = std::ldexp(1.0f, -wexp); a.bias = bias;
   a.bias_bstride = bias_bstride; a.residual = residual; a.div_sqrt2 = div_sqrt2; a.out = out; a.Cout = Cout; a.ldc = ldc;
   a.B = B; a.H = H; a.W = W;
-  if (!ctx->op_splitk) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_splitk), kSplitKScratchElems * sizeof(float)));
+  if (!ctx->op_splitk) {
+    CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_splitk), kSplitKScratchElems * sizeof(float) + 2 * kSplitKCounterTiles * sizeof(unsigned)));
+    CK(cudaMemset(ctx->op_splitk + kSplitKScratchElems, 0, 2 * kSplitKCounterTiles * sizeof(unsigned)));
+  }
   a.splitk_scratch = ctx->op_splitk; a.splitk_scratch_elems = kSplitKScratchElems;
+  a.splitk_counters = reinterpret_cast<unsigned*>(ctx->op_splitk + kSplitKScratchElems);
   std::string e;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
@@ -954,7 +960,6 @@ int flowse_op_attention(flowse_ctx* ctx, int module_idx, const float* x, float* 
   if (ctx->op_scratch_bytes < need) {
     CK(cudaDeviceSynchronize());
     if (ctx->op_scratch) cudaFree(ctx->op_scratch);
-  if (ctx->op_splitk) cudaFree(ctx->op_splitk);
     CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_scratch), need));
     ctx->op_scratch_bytes = need;
   }

@@ -154,8 +154,10 @@ struct ConvGemmArgs {
   double* qstats;               // optional: accumulate quad statistics of the OUTPUT (zeroed buffer)
   float* splitk_scratch;        // optional fp32 scratch enabling split-K for low-resolution layers (may be null)
   size_t splitk_scratch_elems;
+  unsigned* splitk_counters;    // optional [kSplitKCounterTiles][2] zeroed counters enabling the in-kernel reduction
 };
 constexpr size_t kSplitKScratchElems = static_cast<size_t>(148) * 128 * 128;   // enough for any one-wave split
+constexpr int kSplitKCounterTiles = 128;
 // returns 0 on success; fills err otherwise.
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t s, std::string* err);
 // Slow SIMT evaluation of exactly the same operands (debug / cross-check only; never on the product path).
