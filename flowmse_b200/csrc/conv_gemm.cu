@@ -59,6 +59,9 @@ struct Cfg {
   static constexpr int STG_BYTES = kEpiWarps * 32 * STG_STRIDE * 4;
   static constexpr int COLS_PER_WARP = (BN >= 32) ? BN / 2 : BN;   // each quadrant's columns are split over 2 warps
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024;
+  // cluster split-K: fp32 tile [128][BN + 4] parked in the operand stages (+4 floats: conflict-free row-wise float4 stores)
+  static constexpr int RED_STRIDE = BN + 4;
+  static_assert(BM * RED_STRIDE * 4 <= STAGES * STAGE_BYTES, "reduction tile must fit in the operand stages");
 };
 
 struct GemmParams {
@@ -78,11 +81,81 @@ struct GemmParams {
   int ksplit;
   float* partial;
   long long partial_plane;   // elements per split = B*H*W*ldc
-  // In-kernel reduction (counters != null): the ksplit CTAs of an output tile (co-resident: cooperative launch, grid
-  // <= #SMs) meet at a counter once their partial tiles are in L2, then CTA z sums rows [z*128/S, (z+1)*128/S) of all
-  // partials in fixed z order and applies the epilogue - no second kernel, same deterministic summation order.
-  unsigned* counters;        // [tiles][2] {arrived, departed}, zero between launches
+  // Cluster reduction (cluster_s > 1): the ksplit CTAs of an output tile form ONE thread-block cluster (1,1,S).  Each
+  // parks its raw fp32 accumulator tile in its own shared memory (the operand stages are free by then); after a
+  // cluster barrier CTA z sums rows [z*128/S, (z+1)*128/S) of all S tiles through distributed shared memory
+  // (ld.shared::cluster, fixed z order = the same deterministic summation as the two-pass path) and applies the
+  // epilogue.  No partial planes in global memory, no second kernel.
+  int cluster_s;
 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
+  float4 v;
+  // not volatile / no memory clobber: the peers' tiles are immutable between the two cluster barriers, and the S loads
+  // of a row must be in flight together
+  asm("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr));
+  return v;
+}
+
+struct CtaTile { int b, h0, w0, n0; };
+
+// Split-K cluster reduction of one thread: CTA z of an S-CTA cluster owns rows [z*128/S, (z+1)*128/S) of the tile; warp rg
+// takes every 8th of them, i.e. 16/S rows, so a thread always has 16 remote float4 loads (rows x S peers), all issued
+// before the first is consumed.  Summation order over the peers is fixed (z = 0, 1, ...).
+template <int S, int RED_STRIDE>
+__device__ __forceinline__ void cluster_reduce_rows(const GemmParams& p, const CtaTile& ct, uint32_t red0, int z, int rg,
+                                                    int c4, float& qs_s, float& qs_q) {
+  constexpr int ROWS = BM / S / kEpiWarps;
+  static_assert(ROWS * S == 16, "16 remote loads per thread");
+  const float postf = p.div_sqrt2 ? 0.70710678118654752440f : 1.0f;
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(ct.b) * p.bias_bstride + ct.n0) + c4);
+  long long o[ROWS];
+  float4 rr[ROWS], pv[ROWS][S];
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) {
+    const int r = z * (BM / S) + rg + i * kEpiWarps;
+    const int th = r / p.TW, tw = r - th * p.TW;
+    const int h = ct.h0 + th, w = ct.w0 + tw;
+    o[i] = (h < p.H && w < p.W)
+               ? static_cast<long long>((static_cast<size_t>(ct.b) * p.H + h) * p.W + w) * p.ldc + ct.n0 + 4 * c4 : -1;
+    rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (o[i] >= 0) {
+      if (p.residual) rr[i] = __ldg(reinterpret_cast<const float4*>(p.residual + o[i]));
+      const uint32_t local = red0 + static_cast<uint32_t>((r * RED_STRIDE + 4 * c4) * 4);
+#pragma unroll
+      for (int zz = 0; zz < S; ++zz) pv[i][zz] = ld_dsmem_f4(map_to_cta(local, static_cast<uint32_t>(zz)));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) {
+    if (o[i] < 0) continue;
+    float4 acc = pv[i][0];
+#pragma unroll
+    for (int zz = 1; zz < S; ++zz) { acc.x += pv[i][zz].x; acc.y += pv[i][zz].y; acc.z += pv[i][zz].z; acc.w += pv[i][zz].w; }
+    float4 v;
+    v.x = (acc.x + bv.x + rr[i].x) * postf; v.y = (acc.y + bv.y + rr[i].y) * postf;
+    v.z = (acc.z + bv.z + rr[i].z) * postf; v.w = (acc.w + bv.w + rr[i].w) * postf;
+    *reinterpret_cast<float4*>(p.out + o[i]) = v;
+    qs_s += (v.x + v.y) + (v.z + v.w);
+    qs_q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -245,7 +318,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
       for (int it = 0; it < NIT; ++it) {
         res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.residual && !p.partial && off[it] >= 0 && n0 + col_base + c0 + cj < p.Cout)
+        if (p.residual && !p.partial && p.cluster_s <= 1 && off[it] >= 0 && n0 + col_base + c0 + cj < p.Cout)
           res[it] = __ldg(reinterpret_cast<const float4*>(p.residual + off[it] + c0));
       }
     };
@@ -274,6 +347,17 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
         for (int j = 0; j < CH; ++j)
           r[j] = __float_as_uint((__uint_as_float(r[j]) + __uint_as_float(r2[j])) + __uint_as_float(r3[j]));
+        if (p.cluster_s > 1) {
+          // cluster reduction: park the raw tile (row = TMEM lane) in the now idle operand stages
+          float* red = reinterpret_cast<float*>(smem_raw + (smem_base - ptx::smem_u32(smem_raw))) +
+                       (q * 32 + lane) * C::RED_STRIDE + col_base + c0;
+#pragma unroll
+          for (int j = 0; j < CH; j += 4)
+            *reinterpret_cast<float4*>(red + j) =
+                make_float4(__uint_as_float(r[j]) * p.wscale_inv, __uint_as_float(r[j + 1]) * p.wscale_inv,
+                            __uint_as_float(r[j + 2]) * p.wscale_inv, __uint_as_float(r[j + 3]) * p.wscale_inv);
+          continue;
+        }
         __syncwarp();                                // previous pass has finished reading the staging tile
 #pragma unroll
         for (int j = 0; j < CH; j += 4)
@@ -333,75 +417,45 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   }
 
-  if (p.counters && warp >= 2) {
-    // ---------------------------------------------------------------- in-kernel split-K reduction (epilogue warps)
+  if (p.cluster_s > 1) {
+    // ---------------------------------------------------------------- split-K reduction through distributed smem
     __shared__ float s_red[kEpiWarps][32][2];
-    const int etid = threadIdx.x - 64;
-    const int S = p.ksplit;
-    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-    unsigned* cnt = p.counters + 2 * tile;
-    __threadfence();                                       // this thread's partial stores are visible device-wide
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (etid == 0) {
-      atomicAdd(cnt, 1u);
-      unsigned v = 0;
-      unsigned long long t0 = 0;
-      for (unsigned it = 0;; ++it) {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
-        if (v >= static_cast<unsigned>(S)) break;
-        if ((it & 0xff) == 0xff) {                        // bounded: a scheduling problem traps instead of hanging
-          const unsigned long long now = ptx::globaltimer_ns();
-          if (t0 == 0) t0 = now; else if (now - t0 > 4000000000ull) __trap();
+    const int S = p.cluster_s;
+    __syncwarp();
+    cluster_sync_all();                                    // every CTA's tile is parked and visible cluster-wide
+    if (threadIdx.x == 64) stamp(6);
+    if (warp >= 2) {
+      const int etid = threadIdx.x - 64;
+      const int z = static_cast<int>(cluster_ctarank());
+      const int ncol4 = min(BN, p.Cout - n0) >> 2;         // float4 columns of this tile
+      const int c4 = etid & 31, rg = etid >> 5;            // fixed column quad per thread, 8 row groups
+      const uint32_t red0 = smem_base;
+      float qs_s = 0.f, qs_q = 0.f;
+      if (c4 < ncol4) {
+        const CtaTile ct{b, h0, w0, n0};
+        switch (S) {
+          case 2: cluster_reduce_rows<2, C::RED_STRIDE>(p, ct, red0, z, rg, c4, qs_s, qs_q); break;
+          case 4: cluster_reduce_rows<4, C::RED_STRIDE>(p, ct, red0, z, rg, c4, qs_s, qs_q); break;
+          case 8: cluster_reduce_rows<8, C::RED_STRIDE>(p, ct, red0, z, rg, c4, qs_s, qs_q); break;
+          default: cluster_reduce_rows<16, C::RED_STRIDE>(p, ct, red0, z, rg, c4, qs_s, qs_q); break;
         }
       }
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    __threadfence();
-    const int z = blockIdx.z;
-    const int r_lo = (z * BM) / S, r_hi = ((z + 1) * BM) / S;
-    const int ncol4 = min(BN, p.Cout - n0) >> 2;           // float4 columns of this tile
-    const int c4 = etid & 31, rg = etid >> 5;              // fixed column quad per thread, 8 row groups
-    const float postf = p.div_sqrt2 ? 0.70710678118654752440f : 1.0f;
-    float qs_s = 0.f, qs_q = 0.f;
-    if (c4 < ncol4) {
-      const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(b) * p.bias_bstride + n0) + c4);
-      for (int r = r_lo + rg; r < r_hi; r += kEpiWarps) {
-        const int th = r / p.TW, tw = r - th * p.TW;
-        const int h = h0 + th, w = w0 + tw;
-        if (h >= p.H || w >= p.W) continue;
-        const long long o = static_cast<long long>((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.ldc + n0 + 4 * c4;
-        float4 acc = __ldcg(reinterpret_cast<const float4*>(p.partial + o));
-        for (int zz = 1; zz < S; ++zz) {
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(p.partial + zz * p.partial_plane + o));
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
-        float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.residual) rr = __ldg(reinterpret_cast<const float4*>(p.residual + o));
-        float4 v;
-        v.x = (acc.x + bv.x + rr.x) * postf; v.y = (acc.y + bv.y + rr.y) * postf;
-        v.z = (acc.z + bv.z + rr.z) * postf; v.w = (acc.w + bv.w + rr.w) * postf;
-        *reinterpret_cast<float4*>(p.out + o) = v;
-        qs_s += (v.x + v.y) + (v.z + v.w);
-        qs_q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-      }
-    }
-    if (p.qstats) {
-      s_red[rg][c4][0] = qs_s; s_red[rg][c4][1] = qs_q;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (etid < ncol4) {
-        float as = 0.f, aq = 0.f;
+      if (p.qstats) {
+        s_red[rg][c4][0] = qs_s; s_red[rg][c4][1] = qs_q;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (etid < ncol4) {
+          float as = 0.f, aq = 0.f;
 #pragma unroll
-        for (int g = 0; g < kEpiWarps; ++g) { as += s_red[g][etid][0]; aq += s_red[g][etid][1]; }
-        double* dst = qstat_slot(p.qstats, b, tile * S + z, p.Cout >> 2) + static_cast<size_t>((n0 >> 2) + etid) * 2;
-        atomicAdd(dst, static_cast<double>(as));
-        atomicAdd(dst + 1, static_cast<double>(aq));
+          for (int g = 0; g < kEpiWarps; ++g) { as += s_red[g][etid][0]; aq += s_red[g][etid][1]; }
+          const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+          double* dst = qstat_slot(p.qstats, b, tile * S + z, p.Cout >> 2) + static_cast<size_t>((n0 >> 2) + etid) * 2;
+          atomicAdd(dst, static_cast<double>(as));
+          atomicAdd(dst + 1, static_cast<double>(aq));
+        }
       }
     }
-    // every CTA of the tile has read what it needs once all S have departed: the last one re-arms the counters
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (etid == 0) {
-      if (atomicAdd(cnt + 1, 1u) == static_cast<unsigned>(S - 1)) { cnt[0] = 0u; cnt[1] = 0u; __threadfence(); }
-    }
+    __syncwarp();
+    cluster_sync_all();                                    // no CTA's shared memory goes away while a peer still reads it
   }
 
   if (threadIdx.x == 64) stamp(4);
@@ -576,17 +630,6 @@ bool make_w_map(CUtensorMap* m, const __half* base, int Npad, int K, int BN, std
   return true;
 }
 
-int num_sms_gemm() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
 void choose_tile(int H, int W, int& TW, int& TH) {
   long best = LONG_MAX;
   TW = 128; TH = 1;
@@ -613,7 +656,7 @@ GemmParams make_params(const ConvGemmArgs& a) {
   p.out = a.out;
   p.div_sqrt2 = a.div_sqrt2;
   p.dbg = nullptr;
-  p.ksplit = 1; p.partial = nullptr; p.partial_plane = 0; p.counters = nullptr;
+  p.ksplit = 1; p.partial = nullptr; p.partial_plane = 0; p.cluster_s = 0;
   p.qstats = a.qstats;
   return p;
 }
@@ -628,6 +671,32 @@ bool check_args(const ConvGemmArgs& a, std::string* err) {
   if (!a.bias) return fail("bias is required");
   if (a.B <= 0 || a.H <= 0 || a.W <= 0) return fail("empty problem");
   return true;
+}
+
+// Number of 16-CTA clusters (1,1,16; a non-portable size) of this kernel the device can run concurrently, 0 when the size
+// is not available.  Queried once per instantiation.  Clusters of up to 8 CTAs are always schedulable.
+template <int BN>
+int max_clusters16() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  using C = Cfg<BN>;
+  cached = 0;
+  if (getenv("FLOWSE_CLUSTER16") && getenv("FLOWSE_CLUSTER16")[0] == '0') return cached;
+  if (cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<BN>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return cached;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1, 1, 16); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 16;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, conv_gemm_tcgen05_kernel<BN>, &cfg);
+  if (e != cudaSuccess) cudaGetLastError();
+  cached = (e == cudaSuccess) ? n : 0;
+  return cached;
 }
 
 template <int BN>
@@ -659,29 +728,40 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
     if (S < 2) S = 1;
     if (S > 1) { p.ksplit = S; p.partial = a.splitk_scratch; p.partial_plane = plane; grid.z = S; }
   }
-  // All CTAs fit in one co-resident wave (one CTA per SM), so the reduction CAN run inside the kernel.  Measured on B200
-  // (bench.py, B=1, T=512) it is slower than the separate reduce kernel: 23.83 vs 23.26 ms per sampler call - under
-  // graph replay a kernel boundary costs less than the tile-wide counter wait plus a 256-thread slice reduction.
-  // Opt-in (FLOWSE_SPLITK_FUSED=1) for experiments; the default is the two-pass path.
-  static const bool want_fused = getenv("FLOWSE_SPLITK_FUSED") != nullptr;
-  const bool fused_reduce = want_fused && S > 1 && a.splitk_counters && tiles * S <= num_sms_gemm() &&
-                            tiles <= kSplitKCounterTiles;
-  if (fused_reduce) p.counters = a.splitk_counters;
+  // Cluster reduction: the S CTAs of a tile become one cluster (1,1,S) and reduce through distributed shared memory.
+  // S is capped by the cluster size the device can co-schedule with this kernel's shared-memory footprint (16 is a
+  // non-portable size; 8 is always available).  FLOWSE_SPLITK=2pass keeps the partial-plane + reduce-kernel path.
+  static const int splitk_mode = [] {
+    const char* e = getenv("FLOWSE_SPLITK");
+    return (e && !strcmp(e, "2pass")) ? 0 : 1;
+  }();
+  bool cluster_reduce = false;
+  if (splitk_mode == 1 && tiles <= 74 && nkb_total >= 8) {
+    const int max_cluster = (tiles <= max_clusters16<BN>()) ? 16 : 8;
+    int Sc = std::min(std::min(148 / tiles, nkb_total / 4), max_cluster);
+    while (Sc & (Sc - 1)) Sc &= Sc - 1;                  // cluster sizes: powers of two
+    if (Sc >= 2) {
+      cluster_reduce = true;
+      S = Sc;
+      p.ksplit = S; p.cluster_s = S; p.partial = nullptr; p.partial_plane = 0; grid.z = S;
+    }
+  }
   static const bool dbg = getenv("FLOWSE_CONV_DBG") != nullptr;
   long long* dbuf = nullptr;
-  const size_t ncta = static_cast<size_t>(grid.x) * grid.y;
+  const size_t ncta = static_cast<size_t>(grid.x) * grid.y * grid.z;
   if (dbg) { cudaMalloc(&dbuf, ncta * 8 * sizeof(long long)); cudaMemset(dbuf, 0, ncta * 8 * sizeof(long long)); p.dbg = dbuf; }
-  if (fused_reduce) {
-    // cooperative: the runtime guarantees (or refuses) co-residency of the whole grid, which the counter wait needs
+  if (cluster_reduce) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = static_cast<unsigned>(S);
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 2;
     ++launch_counter();
     cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN>, tmA, tmX, tmW, p);
-    if (le != cudaSuccess) { if (err) *err = std::string("conv_gemm cooperative launch: ") + cudaGetErrorString(le); return 1; }
+    if (le != cudaSuccess) { if (err) *err = std::string("conv_gemm cluster launch: ") + cudaGetErrorString(le); return 1; }
   } else {
     launch_k(conv_gemm_tcgen05_kernel<BN>, grid, dim3(NUM_THREADS), C::SMEM_BYTES, s, tmA, tmX, tmW, p);
   }
@@ -696,11 +776,13 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
       for (int k = 0; k < 5; ++k) ph[k] += static_cast<double>(h[c * 8 + k + 1] - h[c * 8 + k]);
       tmin = std::min(tmin, h[c * 8]); tmax = std::max(tmax, h[c * 8 + 5]);
     }
-    fprintf(stderr, "[conv dbg] ctas=%zu kb=%d  setup %.2f us | first-data %.2f | mainloop %.2f | epilogue %.2f | teardown %.2f | kernel span %.2f us\n",
-            ncta, p.ntaps * p.nchunk_main + p.nchunk_sc, ph[0] / ncta / 1e3, ph[1] / ncta / 1e3, ph[2] / ncta / 1e3,
-            ph[3] / ncta / 1e3, ph[4] / ncta / 1e3, (tmax - tmin) / 1e3);
+    double park = 0.0;
+    if (cluster_reduce) for (size_t c = 0; c < ncta; ++c) park += static_cast<double>(h[c * 8 + 6] - h[c * 8 + 3]);
+    fprintf(stderr, "[conv dbg] grid=(%u,%u,%u) kb=%d  setup %.2f us | first-data %.2f | mainloop %.2f | epilogue %.2f (park+cluster barrier %.2f) | teardown %.2f | kernel span %.2f us\n",
+            grid.x, grid.y, grid.z, p.ntaps * p.nchunk_main + p.nchunk_sc, ph[0] / ncta / 1e3, ph[1] / ncta / 1e3, ph[2] / ncta / 1e3,
+            ph[3] / ncta / 1e3, park / ncta / 1e3, ph[4] / ncta / 1e3, (tmax - tmin) / 1e3);
   }
-  if (S > 1 && !fused_reduce) {
+  if (S > 1 && !cluster_reduce) {
     const int n4b = a.H * a.W * a.ldc / 4;
     const bool can_stats = a.qstats && (256 % (a.ldc / 4) == 0);
     dim3 rgrid((n4b + 255) / 256, a.B);

@@ -114,7 +114,7 @@ struct AttnW {
   float *gn_g = nullptr, *gn_b = nullptr, *wqkv = nullptr, *bqkv = nullptr, *w3 = nullptr, *b3 = nullptr;
 };
 struct CombW { int c = 0; float *w = nullptr, *b = nullptr; };
-struct HeadW { int c = 0; float *gn_g = nullptr, *gn_b = nullptr, *bias = nullptr; ConvW conv; };
+struct HeadW { int c = 0; float *gn_g = nullptr, *gn_b = nullptr, *bias = nullptr, *wf = nullptr; };   // wf: [9][C][4] fp32
 
 struct Act { float* p = nullptr; int C = 0, H = 0, W = 0; double* qs = nullptr; };   // qs: quad statistics [B][C/4][2]
 
@@ -296,7 +296,12 @@ int load_weights_impl(flowse_ctx* ctx, const HostBlob& hb) {
       GET(g, P(i) + "weight", m.cin); GET(b, P(i) + "bias", m.cin);
       GET(cw, P(i + 1) + "weight", 9LL * m.cin * 4); GET(cb, P(i + 1) + "bias", 4);
       if (up_f32(ctx, g, m.cin, &h.gn_g) || up_f32(ctx, b, m.cin, &h.gn_b) || up_f32(ctx, cb, 4, &h.bias)) return 1;
-      if (upload_conv(ctx, cw, 4, m.cin, 9, nullptr, 0, 16, &h.conv)) return 1;
+      // PyTorch [4][C][3][3] -> tap-major [9][C][4] (the 4 outputs of one input channel contiguous) for head_conv_kernel
+      std::vector<float> wf(static_cast<size_t>(9) * m.cin * 4);
+      for (int o = 0; o < 4; ++o)
+        for (int c = 0; c < m.cin; ++c)
+          for (int t = 0; t < 9; ++t) wf[(static_cast<size_t>(t) * m.cin + c) * 4 + o] = cw[(static_cast<size_t>(o) * m.cin + c) * 9 + t];
+      if (up_f32(ctx, wf.data(), wf.size(), &h.wf)) return 1;
       ctx->heads[i] = h;
     }
   }
@@ -346,9 +351,8 @@ struct Builder {
   int stat_slots = 0;
   // scratch
   __half *scrA = nullptr, *scrX = nullptr;
-  float *scrH1 = nullptr, *scrF = nullptr, *scrQKV = nullptr, *scrS = nullptr, *scrO = nullptr, *scrHead = nullptr;
+  float *scrH1 = nullptr, *scrF = nullptr, *scrQKV = nullptr, *scrS = nullptr, *scrO = nullptr;
   float *temb_act = nullptr, *bias_table = nullptr, *splitk = nullptr;
-  unsigned* splitk_cnt = nullptr;
 
   void push(int nk, std::function<int(cudaStream_t)> fn, int kind = 0, double flops = 0.0, int i0 = 0, int i1 = 0,
             int i2 = 0, int i3 = 0) {
@@ -392,7 +396,7 @@ struct Builder {
     c0.wscale_inv = r.conv0.wscale_inv; c0.bias = bias_table + r.dense_off; c0.bias_bstride = ctx->dense_rows;
     c0.residual = nullptr; c0.div_sqrt2 = 0; c0.out = scrH1; c0.Cout = r.cout; c0.ldc = r.cout;
     c0.B = B; c0.H = Ho; c0.W = Wo;
-    c0.splitk_scratch = splitk; c0.splitk_scratch_elems = kSplitKScratchElems; c0.splitk_counters = splitk_cnt; c0.qstats = st1;
+    c0.splitk_scratch = splitk; c0.splitk_scratch_elems = kSplitKScratchElems; c0.qstats = st1;
     { flowse_ctx* cx = ctx; push(2, [=](cudaStream_t s) { return run_conv(cx, c0, s); }, 3, conv_flops(c0), c0.H, c0.W, c0.ntaps * c0.Cin + (c0.X ? c0.Cin2 : 0), c0.Cout); }
     float* h1 = scrH1; const int Co = r.cout;
     PrepArgs pb{};
@@ -404,7 +408,7 @@ struct Builder {
     c1.Wp = r.conv1.wp; c1.Npad = r.conv1.Npad; c1.wscale_inv = r.conv1.wscale_inv; c1.bias = r.bias1;
     c1.bias_bstride = 0; c1.residual = r.has_sc ? nullptr : s1; c1.div_sqrt2 = 1; c1.out = out.p; c1.Cout = Co;
     c1.ldc = Co; c1.B = B; c1.H = Ho; c1.W = Wo;
-    c1.splitk_scratch = splitk; c1.splitk_scratch_elems = kSplitKScratchElems; c1.splitk_counters = splitk_cnt; c1.qstats = out.qs;
+    c1.splitk_scratch = splitk; c1.splitk_scratch_elems = kSplitKScratchElems; c1.qstats = out.qs;
     { flowse_ctx* cx = ctx; push(2, [=](cudaStream_t s) { return run_conv(cx, c1, s); }, 3, conv_flops(c1), c1.H, c1.W, c1.ntaps * c1.Cin + (c1.X ? c1.Cin2 : 0), c1.Cout); }
     plan->taps[mi] = out;
     return out;
@@ -468,9 +472,7 @@ struct Builder {
     scrQKV = ar.alloc<float>(static_cast<size_t>(B) * La * 768);
     scrS = ar.alloc<float>(static_cast<size_t>(B) * La * La);
     scrO = ar.alloc<float>(static_cast<size_t>(B) * La * 256);
-    scrHead = ar.alloc<float>(top * 4);
     splitk = ar.alloc<float>(kSplitKScratchElems);
-    splitk_cnt = ar.alloc<unsigned>(2 * kSplitKCounterTiles);      // arena is zero-initialised; the kernel re-arms them
     plan->stats_bytes = static_cast<size_t>(kMaxStatSlots) * B * kStatSlotDoubles * sizeof(double);
     plan->stats = ar.alloc<double>(plan->stats_bytes / sizeof(double));
     plan->gn_partials = ar.alloc<double>(static_cast<size_t>(B) * gn_stats_max_blocks() * 256);
@@ -532,18 +534,12 @@ struct Builder {
       {
         const HeadW& hw = ctx->heads.at(m);
         const float* hp = h.p; const int C = h.C, Hh = h.H, Ww = h.W, Bc = B;
-        PrepArgs pa{};
-        pa.src1 = hp; pa.C1 = C; pa.qs1 = h.qs; pa.gamma = hw.gn_g; pa.beta = hw.gn_b; pa.B = B; pa.H = Hh; pa.W = Ww;
-        pa.mode = kPrepPlain; pa.silu = 1; pa.outA = scrA;
-        push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; }, 2);
-        ConvGemmArgs c{};
-        c.A = scrA; c.Cin = C; c.ntaps = 9; c.Wp = hw.conv.wp; c.Npad = hw.conv.Npad; c.wscale_inv = hw.conv.wscale_inv;
-        c.bias = hw.bias; c.bias_bstride = 0; c.out = scrHead; c.Cout = 4; c.ldc = 4; c.B = B; c.H = Hh; c.W = Ww;
-        c.splitk_scratch = splitk; c.splitk_scratch_elems = kSplitKScratchElems; c.splitk_counters = splitk_cnt;
-        { flowse_ctx* cx = ctx; push(2, [=](cudaStream_t s) { return run_conv(cx, c, s); }, 3, conv_flops(c), c.H, c.W, c.ntaps * c.Cin + (c.X ? c.Cin2 : 0), c.Cout); }
         float4* pyr = ar.alloc<float4>(static_cast<size_t>(B) * Hh * Ww);
-        const float4* prev = pyr_prev; const float4* head = reinterpret_cast<const float4*>(scrHead);
-        push(1, [=](cudaStream_t s) { launch_pyr_accum(prev, head, pyr, Bc, Hh, Ww, s); return 0; }, 5);
+        const float4* prev = pyr_prev; const double* hq = h.qs;
+        const float *gg = hw.gn_g, *gb = hw.gn_b, *wf = hw.wf, *hb = hw.bias;
+        // GN + SiLU + conv3x3(C -> 4) + FIR-up(previous level) in one fp32 SIMT kernel
+        push(1, [=](cudaStream_t s) { launch_head_conv(hp, hq, gg, gb, wf, hb, prev, pyr, Bc, Hh, Ww, C, s); return 0; },
+             5, 2.0 * Bc * Hh * Ww * 4 * 9.0 * C, Hh, Ww, 9 * C, 4);
         Act tp; tp.p = reinterpret_cast<float*>(pyr); tp.C = 4; tp.H = Hh; tp.W = Ww;
         plan->taps[m + 1] = tp;
         pyr_prev = pyr;
@@ -932,11 +928,9 @@ int flowse_op_conv_gemm(flowse_ctx* ctx, const void* A, int Cin, int ntaps, cons
   a.bias_bstride = bias_bstride; a.residual = residual; a.div_sqrt2 = div_sqrt2; a.out = out; a.Cout = Cout; a.ldc = ldc;
   a.B = B; a.H = H; a.W = W;
   if (!ctx->op_splitk) {
-    CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_splitk), kSplitKScratchElems * sizeof(float) + 2 * kSplitKCounterTiles * sizeof(unsigned)));
-    CK(cudaMemset(ctx->op_splitk + kSplitKScratchElems, 0, 2 * kSplitKCounterTiles * sizeof(unsigned)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&ctx->op_splitk), kSplitKScratchElems * sizeof(float)));
   }
   a.splitk_scratch = ctx->op_splitk; a.splitk_scratch_elems = kSplitKScratchElems;
-  a.splitk_counters = reinterpret_cast<unsigned*>(ctx->op_splitk + kSplitKScratchElems);
   std::string e;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;

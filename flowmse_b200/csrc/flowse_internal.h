@@ -131,6 +131,11 @@ struct PrepArgs {
 };
 void launch_gn_prep(const PrepArgs& a, cudaStream_t s);
 
+// Fused pyramid head (ncsnpp.py:347-366): out = FIR-up(prev) + conv3x3(C -> 4)(SiLU(GN(h))) + bias, fp32 SIMT.
+// wf: [9][C][4] fp32 (tap-major); prev: coarser pyramid level [B][H/2][W/2] or null; C % 64 == 0.
+void launch_head_conv(const float* h, const double* qs, const float* gamma, const float* beta, const float* wf,
+                      const float* bias, const float4* prev, float4* out, int B, int H, int W, int C, cudaStream_t s);
+
 // ---------------------------------------------------------------------------------------------
 // Implicit-GEMM convolution on tcgen05 (conv_gemm.cu)
 // ---------------------------------------------------------------------------------------------
@@ -154,10 +159,8 @@ struct ConvGemmArgs {
   double* qstats;               // optional: accumulate quad statistics of the OUTPUT (zeroed buffer)
   float* splitk_scratch;        // optional fp32 scratch enabling split-K for low-resolution layers (may be null)
   size_t splitk_scratch_elems;
-  unsigned* splitk_counters;    // optional [kSplitKCounterTiles][2] zeroed counters enabling the in-kernel reduction
 };
 constexpr size_t kSplitKScratchElems = static_cast<size_t>(148) * 128 * 128;   // enough for any one-wave split
-constexpr int kSplitKCounterTiles = 128;
 // returns 0 on success; fills err otherwise.
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t s, std::string* err);
 // Slow SIMT evaluation of exactly the same operands (debug / cross-check only; never on the product path).

@@ -177,6 +177,9 @@ __device__ __forceinline__ void load_stats(const PrepK& k, int b, float* s_mean,
 }
 
 // Plain (no resampling): 8 channels per thread, two pixels per loop trip (4 x 16-byte loads in flight).
+// gamma / beta and the first trip's activations are requested BEFORE the statistics are assembled: at the low
+// resolutions the kernel is one dependent-load chain (statistics -> affine parameters -> activations), and the three
+// round trips overlap this way.
 __global__ void __launch_bounds__(256)
 gn_prep_plain_kernel(const PrepK k) {
   pdl_launch_dependents();
@@ -186,26 +189,49 @@ gn_prep_plain_kernel(const PrepK k) {
   const int ppi = blockDim.x / c8;
   const int b = blockIdx.y;
   __shared__ float s_mean[kGroups], s_rstd[kGroups];
-  load_stats(k, b, s_mean, s_rstd);
   const int v = threadIdx.x % c8;
   const int pp = threadIdx.x / c8;
-  if (pp >= ppi) return;
+  const bool active = pp < ppi;
   const int c = v << 3;
-  float4 sc0, sh0, sc1, sh1;
-  scale_shift(k, s_mean, s_rstd, c, C / kGroups, sc0, sh0);
-  scale_shift(k, s_mean, s_rstd, c + 4, C / kGroups, sc1, sh1);
   const int npix = k.H * k.W;
   const float* src; int ld;
   if (c < k.C1) { src = k.s1 + c; ld = k.C1; } else { src = k.s2 + (c - k.C1); ld = k.C2; }
   src += static_cast<size_t>(b) * npix * ld;
+  const int stride = gridDim.x * ppi;
+  int p = blockIdx.x * ppi + pp;
+  const bool has_one = active && p < npix, has_two = active && p + stride < npix;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 ga0 = zero4, ga1 = zero4, be0 = zero4, be1 = zero4, x0 = zero4, x1 = zero4, z0 = zero4, z1 = zero4;
+  if (active) {
+    ga0 = __ldg(reinterpret_cast<const float4*>(k.gamma + c)); ga1 = __ldg(reinterpret_cast<const float4*>(k.gamma + c + 4));
+    be0 = __ldg(reinterpret_cast<const float4*>(k.beta + c)); be1 = __ldg(reinterpret_cast<const float4*>(k.beta + c + 4));
+  }
+  if (has_one) {
+    const float* a = src + static_cast<size_t>(p) * ld;
+    x0 = __ldg(reinterpret_cast<const float4*>(a)); x1 = __ldg(reinterpret_cast<const float4*>(a + 4));
+  }
+  if (has_two) {
+    const float* a = src + static_cast<size_t>(p + stride) * ld;
+    z0 = __ldg(reinterpret_cast<const float4*>(a)); z1 = __ldg(reinterpret_cast<const float4*>(a + 4));
+  }
+  load_stats(k, b, s_mean, s_rstd);
+  if (!has_one) return;
+  float4 sc0, sh0, sc1, sh1;
+  {
+    const int cpg = C / kGroups;
+    const float m0 = s_mean[c / cpg], r0 = s_rstd[c / cpg], m1 = s_mean[(c + 4) / cpg], r1 = s_rstd[(c + 4) / cpg];
+    sc0.x = r0 * ga0.x; sc0.y = r0 * ga0.y; sc0.z = r0 * ga0.z; sc0.w = r0 * ga0.w;
+    sh0.x = fmaf(-m0, sc0.x, be0.x); sh0.y = fmaf(-m0, sc0.y, be0.y); sh0.z = fmaf(-m0, sc0.z, be0.z); sh0.w = fmaf(-m0, sc0.w, be0.w);
+    sc1.x = r1 * ga1.x; sc1.y = r1 * ga1.y; sc1.z = r1 * ga1.z; sc1.w = r1 * ga1.w;
+    sh1.x = fmaf(-m1, sc1.x, be1.x); sh1.y = fmaf(-m1, sc1.y, be1.y); sh1.z = fmaf(-m1, sc1.z, be1.z); sh1.w = fmaf(-m1, sc1.w, be1.w);
+  }
   const size_t obase = static_cast<size_t>(b) * npix * C + c;
   const size_t plane = static_cast<size_t>(k.B) * npix * C;
-  const int stride = gridDim.x * ppi;
 
-  auto emit = [&](int p, const float4 x0, const float4 x1) {
-    const float4 y0 = norm_act(x0, sc0, sh0, k.silu);
-    const float4 y1 = norm_act(x1, sc1, sh1, k.silu);
-    const size_t o = obase + static_cast<size_t>(p) * C;
+  auto emit = [&](int pi, const float4 a0, const float4 a1) {
+    const float4 y0 = norm_act(a0, sc0, sh0, k.silu);
+    const float4 y1 = norm_act(a1, sc1, sh1, k.silu);
+    const size_t o = obase + static_cast<size_t>(pi) * C;
     if (k.outA) {
       uint2 h0, l0, h1, l1;
       split4(y0, h0, l0); split4(y1, h1, l1);
@@ -214,20 +240,23 @@ gn_prep_plain_kernel(const PrepK k) {
     }
     if (k.outX) {
       uint2 h0, l0, h1, l1;
-      split4(x0, h0, l0); split4(x1, h1, l1);
+      split4(a0, h0, l0); split4(a1, h1, l1);
       *reinterpret_cast<uint4*>(k.outX + o) = pack8(h0, h1);
       *reinterpret_cast<uint4*>(k.outX + plane + o) = pack8(l0, l1);
     }
     if (k.outF) { *reinterpret_cast<float4*>(k.outF + o) = y0; *reinterpret_cast<float4*>(k.outF + o + 4) = y1; }
-    if (k.outXF) { *reinterpret_cast<float4*>(k.outXF + o) = x0; *reinterpret_cast<float4*>(k.outXF + o + 4) = x1; }
+    if (k.outXF) { *reinterpret_cast<float4*>(k.outXF + o) = a0; *reinterpret_cast<float4*>(k.outXF + o + 4) = a1; }
   };
 
-  int p = blockIdx.x * ppi + pp;
+  emit(p, x0, x1);
+  if (!has_two) return;
+  emit(p + stride, z0, z1);
+  p += 2 * stride;
   for (; p + stride < npix; p += 2 * stride) {
     const float* a = src + static_cast<size_t>(p) * ld;
     const float* bq = src + static_cast<size_t>(p + stride) * ld;
-    const float4 x0 = __ldg(reinterpret_cast<const float4*>(a)), x1 = __ldg(reinterpret_cast<const float4*>(a + 4));
-    const float4 z0 = __ldg(reinterpret_cast<const float4*>(bq)), z1 = __ldg(reinterpret_cast<const float4*>(bq + 4));
+    x0 = __ldg(reinterpret_cast<const float4*>(a)); x1 = __ldg(reinterpret_cast<const float4*>(a + 4));
+    z0 = __ldg(reinterpret_cast<const float4*>(bq)); z1 = __ldg(reinterpret_cast<const float4*>(bq + 4));
     emit(p, x0, x1);
     emit(p + stride, z0, z1);
   }
@@ -346,6 +375,208 @@ gn_prep_resample_kernel(const PrepK k) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Pyramid head, fully fused: pyr = FIR-up(prev) + conv3x3(C -> 4)(SiLU(GN(h))) + bias
+// (/root/reference/flowmse/backbones/ncsnpp.py:347-366; FIR closed form as in pyr_accum).
+// Cout = 4 is the wrong shape for the tensor cores (a 128 x 16 MMA tile is 3/4 padding and still needs the
+// fp16 hi/lo operand pass over h); here ONE kernel reads h (fp32) once, normalises + activates it into a shared-memory
+// halo tile, and evaluates the 4 outputs with exact fp32 FMAs.  Output tile (RG*P) x TW pixels; a thread owns P vertically
+// adjacent pixels x 4 outputs and, per (dx, channel quad), loads the P + 2 activation rows it needs once for all 3 dy
+// taps; the channels of a chunk are split over KS thread groups whose partial sums are folded through shared memory in
+// a fixed order.  Two shapes: 16 x 16 tiles with P = 4 for the full-resolution level (FMA-bound, 1.27x halo, 512 CTAs at
+// B = 1), 4 x 8 tiles with P = 1 and an 8-way channel split for every smaller level (latency-bound: many short CTAs).
+// ---------------------------------------------------------------------------------------------
+struct HeadK {
+  const float* h; const double* qs; const float* gamma; const float* beta;
+  const float* wf;        // [9][C][4] fp32: tap-major, the 4 outputs of one input channel contiguous
+  const float* bias;      // [4]
+  const float4* prev;     // [B][H/2][W/2] previous (coarser) pyramid level or null
+  float4* out;            // [B][H][W]
+  int B, H, W, C;
+};
+
+template <int TW, int RG, int P, int KS, int CC>
+__global__ void __launch_bounds__(TW * RG * KS)
+head_conv_kernel(const HeadK k) {
+  constexpr int TH = RG * P;
+  constexpr int NT = TW * RG * KS;
+  constexpr int RW = TW + 2, RH = TH + 2;
+  constexpr int PS = CC + 4;                       // floats per staged pixel (+4: conflict-free float4 rows)
+  constexpr int CPK = CC / KS;                     // channels of a chunk per thread group
+  static_assert(CPK % 4 == 0 && CPK >= 4, "channel split");
+  extern __shared__ __align__(16) float sm[];
+  constexpr int TILE_F = (RH * RW * PS > KS * TH * TW * 4) ? RH * RW * PS : KS * TH * TW * 4;
+  float* s_act = sm;                               // [RH*RW][PS]; reused for the [KS][TH*TW] float4 partial sums
+  float* s_w = s_act + TILE_F;                     // [9][CC][4]
+  float* s_sc = s_w + 9 * CC * 4;                  // [C] scale, [C] shift
+  __shared__ float s_mean[kGroups], s_rstd[kGroups];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  const int C = k.C;
+  const int tiles_w = (k.W + TW - 1) / TW;
+  const int b = blockIdx.y;
+  const int h0 = (blockIdx.x / tiles_w) * TH, w0 = (blockIdx.x % tiles_w) * TW;
+  {
+    PrepK pk{};
+    pk.C1 = C; pk.C2 = 0; pk.qs1 = k.qs; pk.qs2 = nullptr; pk.H = k.H; pk.W = k.W;
+    load_stats(pk, b, s_mean, s_rstd);
+    pk.gamma = k.gamma; pk.beta = k.beta;
+    float* s_sh = s_sc + C;
+    for (int c = tid * 4; c < C; c += NT * 4) {
+      float4 sc, sh;
+      scale_shift(pk, s_mean, s_rstd, c, C / kGroups, sc, sh);
+      *reinterpret_cast<float4*>(s_sc + c) = sc;
+      *reinterpret_cast<float4*>(s_sh + c) = sh;
+    }
+  }
+  const float* s_sh = s_sc + C;
+  const int ks = tid / (TW * RG);
+  const int rgp = (tid / TW) % RG;
+  const int col = tid % TW;
+  float acc[P][4];
+#pragma unroll
+  for (int i = 0; i < P; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+  const float* src = k.h + static_cast<size_t>(b) * k.H * k.W * C;
+
+  for (int c0 = 0; c0 < C; c0 += CC) {
+    __syncthreads();                               // previous chunk fully consumed (and s_sc complete on the first trip)
+    // all global loads of this chunk (activations and weights) are issued before the first one is consumed: the small
+    // levels are pure latency chains, one round trip per chunk instead of one per element
+    constexpr int L = CC / 4;
+    constexpr int NPA = (RH * RW * L + NT - 1) / NT;
+    constexpr int NPW = (9 * CC + NT - 1) / NT;
+    float4 xr[NPA], wr[NPW];
+    bool inb[NPA];
+#pragma unroll
+    for (int it = 0; it < NPA; ++it) {
+      const int idx = tid + it * NT;
+      const int px = idx / L, c4 = idx - px * L;
+      const int r = px / RW, q = px - r * RW;
+      const int hh = h0 - 1 + r, ww = w0 - 1 + q;
+      inb[it] = idx < RH * RW * L && hh >= 0 && hh < k.H && ww >= 0 && ww < k.W;
+      xr[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (inb[it])
+        xr[it] = __ldg(reinterpret_cast<const float4*>(src + (static_cast<size_t>(hh) * k.W + ww) * C + c0 + c4 * 4));
+    }
+#pragma unroll
+    for (int it = 0; it < NPW; ++it) {
+      const int idx = tid + it * NT;
+      wr[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < 9 * CC) {
+        const int tap = idx / CC, c = idx - tap * CC;
+        wr[it] = __ldg(reinterpret_cast<const float4*>(k.wf + (static_cast<size_t>(tap) * C + c0 + c) * 4));
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NPA; ++it) {
+      const int idx = tid + it * NT;
+      if (idx < RH * RW * L) {
+        const int px = idx / L, c4 = idx - px * L;
+        const int c = c0 + c4 * 4;
+        // the conv pads the ACTIVATED tensor with zeros
+        const float4 y = inb[it] ? norm_act(xr[it], *reinterpret_cast<const float4*>(s_sc + c),
+                                            *reinterpret_cast<const float4*>(s_sh + c), 1)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(s_act + px * PS + c4 * 4) = y;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NPW; ++it) {
+      const int idx = tid + it * NT;
+      if (idx < 9 * CC) *reinterpret_cast<float4*>(s_w + idx * 4) = wr[it];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int cq = 0; cq < CPK / 4; ++cq) {
+      const int cc = ks * CPK + cq * 4;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        float4 a[P + 2];
+#pragma unroll
+        for (int r = 0; r < P + 2; ++r)
+          a[r] = *reinterpret_cast<const float4*>(s_act + ((rgp * P + r) * RW + col + dx) * PS + cc);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const float* wp = s_w + ((dy * 3 + dx) * CC + cc) * 4;
+          const float4 wa = *reinterpret_cast<const float4*>(wp), wb = *reinterpret_cast<const float4*>(wp + 4);
+          const float4 wc = *reinterpret_cast<const float4*>(wp + 8), wd = *reinterpret_cast<const float4*>(wp + 12);
+#pragma unroll
+          for (int i = 0; i < P; ++i) {
+            const float4 v = a[i + dy];
+            acc[i][0] = fmaf(v.x, wa.x, acc[i][0]); acc[i][1] = fmaf(v.x, wa.y, acc[i][1]);
+            acc[i][2] = fmaf(v.x, wa.z, acc[i][2]); acc[i][3] = fmaf(v.x, wa.w, acc[i][3]);
+            acc[i][0] = fmaf(v.y, wb.x, acc[i][0]); acc[i][1] = fmaf(v.y, wb.y, acc[i][1]);
+            acc[i][2] = fmaf(v.y, wb.z, acc[i][2]); acc[i][3] = fmaf(v.y, wb.w, acc[i][3]);
+            acc[i][0] = fmaf(v.z, wc.x, acc[i][0]); acc[i][1] = fmaf(v.z, wc.y, acc[i][1]);
+            acc[i][2] = fmaf(v.z, wc.z, acc[i][2]); acc[i][3] = fmaf(v.z, wc.w, acc[i][3]);
+            acc[i][0] = fmaf(v.w, wd.x, acc[i][0]); acc[i][1] = fmaf(v.w, wd.y, acc[i][1]);
+            acc[i][2] = fmaf(v.w, wd.z, acc[i][2]); acc[i][3] = fmaf(v.w, wd.w, acc[i][3]);
+          }
+        }
+      }
+    }
+  }
+  // fold the KS channel groups in fixed order through shared memory (the activation tile is no longer needed)
+  __syncthreads();
+  float4* s_part = reinterpret_cast<float4*>(sm);  // [KS][TH*TW]
+#pragma unroll
+  for (int i = 0; i < P; ++i)
+    s_part[ks * (TH * TW) + (rgp * P + i) * TW + col] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  __syncthreads();
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(k.bias));
+  for (int px = tid; px < TH * TW; px += NT) {
+    const int h = h0 + px / TW, w = w0 + px % TW;
+    if (h >= k.H || w >= k.W) continue;
+    float4 v = s_part[px];
+#pragma unroll
+    for (int g = 1; g < KS; ++g) {
+      const float4 u = s_part[g * (TH * TW) + px];
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+    if (k.prev) {
+      // StyleGAN2 FIR upsample x2 of the coarser pyramid (taps {1,3,3,9}/16), same arithmetic as pyr_accum
+      const int Hp = k.H >> 1, Wp = k.W >> 1;
+      const int mh = h >> 1, mw = w >> 1;
+      const int h_a = (h & 1) ? mh : mh - 1, h_b = (h & 1) ? mh + 1 : mh;
+      const float wha = (h & 1) ? 3.f : 1.f, whb = (h & 1) ? 1.f : 3.f;
+      const int w_a = (w & 1) ? mw : mw - 1, w_b = (w & 1) ? mw + 1 : mw;
+      const float wwa = (w & 1) ? 3.f : 1.f, wwb = (w & 1) ? 1.f : 3.f;
+      float4 up = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int a2 = 0; a2 < 2; ++a2) {
+        const int hi = a2 ? h_b : h_a;
+        if (hi < 0 || hi >= Hp) continue;
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int wi = c2 ? w_b : w_a;
+          if (wi < 0 || wi >= Wp) continue;
+          const float wgt = (a2 ? whb : wha) * (c2 ? wwb : wwa) * (1.f / 16.f);
+          fma4(up, wgt, __ldg(k.prev + (static_cast<size_t>(b) * Hp + hi) * Wp + wi));
+        }
+      }
+      v.x = up.x + v.x; v.y = up.y + v.y; v.z = up.z + v.z; v.w = up.w + v.w;
+    }
+    k.out[(static_cast<size_t>(b) * k.H + h) * k.W + w] = v;
+  }
+}
+
+template <int TW, int RG, int P, int KS, int CC>
+void launch_head_t(const HeadK& k, cudaStream_t s) {
+  constexpr int TH = RG * P, RW = TW + 2, RH = TH + 2;
+  const size_t tile = std::max(static_cast<size_t>(RH) * RW * (CC + 4), static_cast<size_t>(KS) * TH * TW * 4);
+  const size_t smem = (tile + 9 * CC * 4 + 2 * k.C) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(head_conv_kernel<TW, RG, P, KS, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set = true;
+  }
+  dim3 grid(((k.W + TW - 1) / TW) * ((k.H + TH - 1) / TH), k.B);
+  launch_k(head_conv_kernel<TW, RG, P, KS, CC>, grid, dim3(TW * RG * KS), smem, s, k);
+}
+
 }  // namespace
 
 int gn_stats_max_blocks() { return 296; }
@@ -388,6 +619,13 @@ void launch_gn_prep(const PrepArgs& a, cudaStream_t s) {
     dim3 g((k.Wo + 31) / 32, (k.Ho + 7) / 8, a.B * (C / 32));
     launch_k(gn_prep_resample_kernel<32, 8, 32, false>, g, dim3(256), 0, s, k);
   }
+}
+
+void launch_head_conv(const float* h, const double* qs, const float* gamma, const float* beta, const float* wf,
+                      const float* bias, const float4* prev, float4* out, int B, int H, int W, int C, cudaStream_t s) {
+  HeadK k{h, qs, gamma, beta, wf, bias, prev, out, B, H, W, C};
+  if (static_cast<long>(B) * H * W >= 65536) launch_head_t<16, 4, 4, 4, 16>(k, s);
+  else launch_head_t<8, 4, 1, 8, 128>(k, s);
 }
 
 }  // namespace flowse

@@ -5,8 +5,8 @@
 //
 // TM x 64 tile (TM = 64 or 32, picked so that the few-hundred-token problems still fill the GPU), K step 32,
 // 256 threads, (TM/16) x 4 register micro-tile.  Operands are staged k-major in shared memory so that the inner loop
-// is two 16-byte shared loads per 4 x 4 FMAs; the next K step's global loads are issued into registers before the
-// current step is computed (the problems are latency-bound: K <= 512).
+// is two 16-byte shared loads per 4 x 4 FMAs; the global loads of the next TWO K steps are in flight in registers while
+// the current step is computed (the problems are latency-bound: K <= 512).
 #include "flowse_internal.h"
 
 namespace flowse {
@@ -36,9 +36,9 @@ sgemm_kernel(const SgemmArgs a) {
   const bool vecA = (a.lda % 4 == 0) && ((reinterpret_cast<size_t>(A) & 15) == 0);
   const bool vecB = (a.ldb % 4 == 0) && ((reinterpret_cast<size_t>(Bm) & 15) == 0);
 
-  float4 ra[A_F4], rb[B_F4];
+  float4 ra0[A_F4], rb0[B_F4], ra1[A_F4], rb1[B_F4];     // two K steps of global loads in flight
   // A tile: TM rows x 32 k, row-major in global: float4 f -> row f / 8, k4 = f % 8
-  auto load_a = [&](int k0) {
+  auto load_a = [&](int k0, float4* ra) {
 #pragma unroll
     for (int i = 0; i < A_F4; ++i) {
       const int f = tid + i * 256;
@@ -58,7 +58,7 @@ sgemm_kernel(const SgemmArgs a) {
       ra[i] = v;
     }
   };
-  auto store_a = [&]() {
+  auto store_a = [&](const float4* ra) {
 #pragma unroll
     for (int i = 0; i < A_F4; ++i) {
       const int f = tid + i * 256;
@@ -67,7 +67,7 @@ sgemm_kernel(const SgemmArgs a) {
     }
   };
   // B tile: transB ? [N][K] (float4 along k, stored transposed) : [K][N] (float4 along n, stored as is)
-  auto load_b = [&](int k0) {
+  auto load_b = [&](int k0, float4* rb) {
 #pragma unroll
     for (int i = 0; i < B_F4; ++i) {
       const int f = tid + i * 256;
@@ -102,7 +102,7 @@ sgemm_kernel(const SgemmArgs a) {
       rb[i] = v;
     }
   };
-  auto store_b = [&]() {
+  auto store_b = [&](const float4* rb) {
 #pragma unroll
     for (int i = 0; i < B_F4; ++i) {
       const int f = tid + i * 256;
@@ -117,11 +117,7 @@ sgemm_kernel(const SgemmArgs a) {
   };
 
   float acc[RM][4] = {};
-  load_a(0); load_b(0);
-  for (int k0 = 0; k0 < a.K; k0 += TK) {
-    store_a(); store_b();
-    __syncthreads();
-    if (k0 + TK < a.K) { load_a(k0 + TK); load_b(k0 + TK); }      // in flight while this step is computed
+  auto compute = [&]() {
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
       float av[RM];
@@ -139,6 +135,22 @@ sgemm_kernel(const SgemmArgs a) {
         acc[i][2] = fmaf(av[i], bv.z, acc[i][2]); acc[i][3] = fmaf(av[i], bv.w, acc[i][3]);
       }
     }
+  };
+  // The problems are latency-bound (K <= 512, a handful of CTAs per SM): the loads of K steps s+1 and s+2 are in flight
+  // while step s is computed (two register sets, loop unrolled by two).
+  load_a(0, ra0); load_b(0, rb0);
+  if (TK < a.K) { load_a(TK, ra1); load_b(TK, rb1); }
+  for (int k0 = 0; k0 < a.K; k0 += 2 * TK) {
+    store_a(ra0); store_b(rb0);
+    __syncthreads();
+    if (k0 + 2 * TK < a.K) { load_a(k0 + 2 * TK, ra0); load_b(k0 + 2 * TK, rb0); }
+    compute();
+    __syncthreads();
+    if (k0 + TK >= a.K) break;
+    store_a(ra1); store_b(rb1);
+    __syncthreads();
+    if (k0 + 3 * TK < a.K) { load_a(k0 + 3 * TK, ra1); load_b(k0 + 3 * TK, rb1); }
+    compute();
     __syncthreads();
   }
   const bool vecC = (a.ldc % 4 == 0) && ((reinterpret_cast<size_t>(C) & 15) == 0) &&

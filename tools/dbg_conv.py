@@ -16,3 +16,6 @@ def run(H, W, Cin, Cout, res=False):
     for _ in range(3): ctx.op_conv_gemm(A, Wp, wexp, bias, Cout, residual=r, div_sqrt2=True, out=out)
     torch.cuda.synchronize()
 run(32, 512, 128, 128); run(32, 512, 512, 128); run(256, 512, 128, 128); run(256, 512, 128, 128, True)
+# low-resolution layers (cluster split-K through distributed shared memory)
+print("--- low-res (cluster split-K)", file=sys.stderr)
+run(4, 8, 256, 256); run(8, 16, 256, 256); run(16, 32, 256, 256); run(16, 32, 512, 256); run(32, 64, 256, 256); run(64, 128, 256, 256)
