@@ -757,13 +757,20 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = static_cast<unsigned>(S);
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_mode() >= 1 ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 2;
     ++launch_counter();
     cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN>, tmA, tmX, tmW, p);
     if (le != cudaSuccess) { if (err) *err = std::string("conv_gemm cluster launch: ") + cudaGetErrorString(le); return 1; }
   } else {
-    launch_k(conv_gemm_tcgen05_kernel<BN>, grid, dim3(NUM_THREADS), C::SMEM_BYTES, s, tmA, tmX, tmW, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_mode() >= 1 ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ++launch_counter();
+    cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN>, tmA, tmX, tmW, p);
   }
   if (dbg) {
     cudaStreamSynchronize(s);

@@ -167,6 +167,9 @@ struct flowse_ctx {
   double* op_stats = nullptr; double* op_partials = nullptr; unsigned* op_counters = nullptr;
   float* op_scratch = nullptr; size_t op_scratch_bytes = 0;
   float* op_splitk = nullptr;
+  // STFT / iSTFT (stft.cu): bases built on first use, scratch grown on demand
+  float* stft_basis = nullptr;
+  char* stft_scratch = nullptr; size_t stft_scratch_bytes = 0;
 };
 
 namespace {
@@ -685,6 +688,8 @@ void flowse_destroy(flowse_ctx* ctx) {
   if (ctx->op_counters) cudaFree(ctx->op_counters);
   if (ctx->op_scratch) cudaFree(ctx->op_scratch);
   if (ctx->op_splitk) cudaFree(ctx->op_splitk);
+  if (ctx->stft_basis) cudaFree(ctx->stft_basis);
+  if (ctx->stft_scratch) cudaFree(ctx->stft_scratch);
   delete ctx;
 }
 
@@ -840,7 +845,7 @@ int flowse_set_option(flowse_ctx* ctx, const char* key, int value) {
   const std::string k(key);
   if (k == "conv_impl") ctx->conv_impl = value;
   else if (k == "graph") ctx->use_graph = value;
-  else if (k == "pdl") pdl_enabled() = (value != 0);
+  else if (k == "pdl") pdl_mode() = static_cast<int>(value);
   else { ctx->err = "unknown option '" + k + "'"; return 2; }
   if (ctx->plan) {   // captured graphs bake the old setting
     cudaSetDevice(ctx->device);
@@ -939,6 +944,78 @@ int flowse_op_conv_gemm(flowse_ctx* ctx, const void* A, int Cin, int ntaps, cons
   else rc = launch_conv_gemm(a, st, &e);
   if (rc) ctx->err = e;
   return rc;
+}
+
+// ---- STFT / iSTFT ------------------------------------------------------------------------------
+namespace {
+struct StftScratch { int* lengths; unsigned* peak; float* xpad; long long xpad_stride; float2* S; float* frames; };
+
+int stft_prepare(flowse_ctx* ctx, const int* lengths_host, int B, int min_frames, int* Lmax_out, StftScratch* sc, cudaStream_t s) {
+  if (!lengths_host || B <= 0) { ctx->err = "stft: need B > 0 and a host lengths array"; return 2; }
+  int Lmax = 0;
+  for (int b = 0; b < B; ++b) {
+    if (lengths_host[b] < 256) { ctx->err = "stft: every utterance needs >= 256 samples (reflect padding of n_fft/2 = 255)"; return 2; }
+    Lmax = std::max(Lmax, lengths_host[b]);
+  }
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->stft_basis) {
+    CK(cudaMalloc(reinterpret_cast<void**>(&ctx->stft_basis), stft_basis_floats() * sizeof(float)));
+    launch_stft_basis(ctx->stft_basis, s);
+  }
+  const int Tmax = std::max(stft_frames(Lmax), min_frames);
+  const long long xs = ((static_cast<long long>(Lmax) + 510 + 128 + 127) / 128) * 128;
+  auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+  const size_t o_len = 0, o_peak = up(o_len + sizeof(int) * B), o_xpad = up(o_peak + sizeof(unsigned) * B);
+  const size_t o_S = up(o_xpad + sizeof(float) * B * xs), o_fr = up(o_S + sizeof(float2) * B * Tmax * 256);
+  const size_t need = up(o_fr + sizeof(float) * B * Tmax * 512);
+  if (ctx->stft_scratch_bytes < need) {
+    CK(cudaDeviceSynchronize());
+    if (ctx->stft_scratch) cudaFree(ctx->stft_scratch);
+    CK(cudaMalloc(reinterpret_cast<void**>(&ctx->stft_scratch), need));
+    ctx->stft_scratch_bytes = need;
+  }
+  char* base = ctx->stft_scratch;
+  sc->lengths = reinterpret_cast<int*>(base + o_len); sc->peak = reinterpret_cast<unsigned*>(base + o_peak);
+  sc->xpad = reinterpret_cast<float*>(base + o_xpad); sc->xpad_stride = xs;
+  sc->S = reinterpret_cast<float2*>(base + o_S); sc->frames = reinterpret_cast<float*>(base + o_fr);
+  CK(cudaMemcpyAsync(sc->lengths, lengths_host, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+  *Lmax_out = Lmax;
+  return 0;
+}
+}  // namespace
+
+int flowse_stft_spec(flowse_ctx* ctx, const float* wav, long long wav_stride, const int* lengths_host, int B, int normalize,
+                     float spec_factor, float abs_exponent, void* Y, int Tpad, float* peak_out, void* stream) {
+  if (!ctx) return 2;
+  ctx->err.clear();
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int Lmax = 0; StftScratch sc{};
+  if (int rc = stft_prepare(ctx, lengths_host, B, 0, &Lmax, &sc, s)) return rc;
+  if (!wav || !Y || wav_stride < Lmax) { ctx->err = "stft_spec: null pointer or wav_stride < longest utterance"; return 2; }
+  if (Tpad < stft_frames(Lmax)) { ctx->err = "stft_spec: Tpad is smaller than the frame count of the longest utterance"; return 2; }
+  if (normalize && !peak_out) { ctx->err = "stft_spec: normalize needs peak_out"; return 2; }
+  if (!(spec_factor > 0.f) || !(abs_exponent > 0.f)) { ctx->err = "stft_spec: spec_factor and abs_exponent must be > 0"; return 2; }
+  // the peaks are accumulated as bit patterns directly in the caller's buffer
+  launch_stft_spec(ctx->stft_basis, wav, wav_stride, sc.lengths, B, Lmax, normalize != 0, spec_factor, abs_exponent, sc.xpad,
+                   sc.xpad_stride, sc.S, reinterpret_cast<unsigned*>(peak_out), static_cast<float2*>(Y), Tpad, s);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int flowse_spec_istft(flowse_ctx* ctx, const void* X, int Tpad, const int* lengths_host, int B, float spec_factor,
+                      float abs_exponent, const float* peak, float* wav_out, long long wav_stride, void* stream) {
+  if (!ctx) return 2;
+  ctx->err.clear();
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int Lmax = 0; StftScratch sc{};
+  if (int rc = stft_prepare(ctx, lengths_host, B, Tpad, &Lmax, &sc, s)) return rc;
+  if (!X || !wav_out || wav_stride < Lmax) { ctx->err = "spec_istft: null pointer or wav_stride < longest utterance"; return 2; }
+  if (Tpad < stft_frames(Lmax)) { ctx->err = "spec_istft: Tpad is smaller than the frame count of the longest utterance"; return 2; }
+  if (!(spec_factor > 0.f) || !(abs_exponent > 0.f)) { ctx->err = "spec_istft: spec_factor and abs_exponent must be > 0"; return 2; }
+  launch_spec_istft(ctx->stft_basis, static_cast<const float2*>(X), Tpad, sc.lengths, B, Lmax, spec_factor, abs_exponent, peak,
+                    sc.S, sc.frames, wav_out, wav_stride, s);
+  CK(cudaGetLastError());
+  return 0;
 }
 
 int flowse_op_attention(flowse_ctx* ctx, int module_idx, const float* x, float* out, int B, int H, int W, void* stream) {

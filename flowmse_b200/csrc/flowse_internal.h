@@ -18,11 +18,10 @@ long long& launch_counter();
 //      tensor-map prefetch, weight staging in registers) overlap this kernel;
 //   2. calls pdl_wait() before its first access to global memory another kernel may have produced or may still read
 //      (griddepcontrol.wait returns once all prerequisite grids have COMPLETED and their writes are visible).
-// Every launch goes through launch_k(), which sets cudaLaunchAttributeProgrammaticStreamSerialization; kernels that
-// are not converted must not be launched with it.  Off by default (measured slightly slower under graph replay, see
-// pdl_enabled() in kernels_pointwise.cu); option "pdl" = 1 or FLOWSE_PDL=1 turn it on.
+// launch_k() sets cudaLaunchAttributeProgrammaticStreamSerialization in mode 1 only; the conv_gemm launches set it in
+// modes 1 and 2 (the default: measurements in pdl_mode(), kernels_pointwise.cu).
 // ---------------------------------------------------------------------------------------------
-bool& pdl_enabled();
+int& pdl_mode();      // 0 off, 1 all kernels, 2 low-resolution conv_gemm launches only
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -33,7 +32,7 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_mode() == 1 ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   ++launch_counter();
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
@@ -190,5 +189,21 @@ struct SgemmArgs {
   __half* split_out;                               // optional: also not used (reserved)
 };
 void launch_sgemm(const SgemmArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// Batched STFT / iSTFT + amplitude compression (stft.cu); n_fft 510, hop 128, hann, center=True
+// ---------------------------------------------------------------------------------------------
+size_t stft_basis_floats();                       // forward basis [510][512] + inverse basis [512][512] + window [512]
+void launch_stft_basis(float* basis, cudaStream_t s);
+int stft_frames(int L);                           // 1 + L / 128
+// wav [B][wav_stride] -> Y complex [B][256][Tpad]; scratch: xpad [B][xpad_stride] (xpad_stride >= Lmax + 510 + 128,
+// multiple of 4), S complex [B][frames(Lmax)][256], peak_bits [B] (the peaks as fp32 bit patterns when normalize)
+void launch_stft_spec(const float* basis, const float* wav, long long wav_stride, const int* lengths_dev, int B, int Lmax,
+                      bool normalize, float factor, float expo, float* xpad, long long xpad_stride, float2* S,
+                      unsigned* peak_bits, float2* Y, int Tpad, cudaStream_t s);
+// X complex [B][256][Tpad] -> wav_out [B][wav_stride] (zeros beyond each length); scratch S as above, frames [B][T][512]
+void launch_spec_istft(const float* basis, const float2* X, int Tpad, const int* lengths_dev, int B, int Lmax, float factor,
+                       float expo, const float* peak, float2* S, float* frames, float* wav_out, long long wav_stride,
+                       cudaStream_t s);
 
 }  // namespace flowse

@@ -10,12 +10,15 @@ long long& launch_counter() {
   static long long n = 0;
   return n;
 }
-bool& pdl_enabled() {
-  // Off by default: measured on B200 (bench.py, N=5, B=1, T=512) graph replay is 1.3 % slower with PDL on (26.3 vs
-  // 26.0 ms per sampler call): kernel-to-kernel gaps inside a CUDA graph are already small, and early-scheduled CTAs
-  // of the next kernel compete with the running one.  FLOWSE_PDL=1 / option "pdl" turn it on.
-  static bool on = [] { const char* e = getenv("FLOWSE_PDL"); return e && e[0] == '1'; }();
-  return on;
+int& pdl_mode() {
+  // Programmatic dependent launch: 0 = off, 1 = every kernel, 2 = only the low-resolution conv_gemm launches, whose
+  // prologue (barrier init, TMEM allocation, tensor-map prefetch, ~0.75 us) then overlaps the tail of the small kernel
+  // before them.  Measured on B200 under graph replay (bench.py, B=1, T=512, N=5, two runs each, same box):
+  // mode 0 23.39 / 23.14 ms, mode 2 23.00 / 23.03 ms, mode 1 24.26 / 24.05 ms per sampler call - with every kernel
+  // opted in, early-scheduled CTAs of the next kernel compete with the running persistent kernels.  Default 2;
+  // FLOWSE_PDL=<mode> / option "pdl" select another.
+  static int mode = [] { const char* e = getenv("FLOWSE_PDL"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }();
+  return mode;
 }
 
 namespace {

@@ -57,6 +57,8 @@ def load_library():
     lib.flowse_op_conv_gemm.argtypes = [vp, vp, i, i, vp, i, vp, i, i, vp, i, vp, i, vp, i, i, i, i, i, i, vp]
     lib.flowse_op_conv_gemm.restype = i
     lib.flowse_op_attention.argtypes = [vp, i, vp, vp, i, i, i, vp]; lib.flowse_op_attention.restype = i
+    lib.flowse_stft_spec.argtypes = [vp, vp, ll, C.POINTER(i), i, i, f, f, vp, i, vp, vp]; lib.flowse_stft_spec.restype = i
+    lib.flowse_spec_istft.argtypes = [vp, vp, i, C.POINTER(i), i, f, f, vp, vp, ll, vp]; lib.flowse_spec_istft.restype = i
     _lib = lib
     return lib
 
@@ -65,7 +67,7 @@ EXPORTED_SYMBOLS = [
     "flowse_create", "flowse_destroy", "flowse_last_error", "flowse_load_weights", "flowse_workspace_bytes",
     "flowse_prior_sample", "flowse_ncsnpp_forward", "flowse_euler_step", "flowse_sample", "flowse_set_option",
     "flowse_kernel_launches", "flowse_profile_forward", "flowse_debug_tap", "flowse_debug_copy", "flowse_pack_conv_weights", "flowse_op_gn_prep",
-    "flowse_op_conv_gemm", "flowse_op_attention",
+    "flowse_op_conv_gemm", "flowse_op_attention", "flowse_stft_spec", "flowse_spec_istft",
 ]
 
 
@@ -198,6 +200,50 @@ class Context:
         out = torch.empty_like(y)
         self._check(self._lib.flowse_sample(self._h, y.data_ptr(), _ptr(y_prior), z.data_ptr(), arr, ts.numel(), int(solver),
                                             float(sigma), out.data_ptr(), B, T, _stream()))
+        return out
+
+    # ---- STFT / iSTFT either side of the sampler ----------------------------------
+    @staticmethod
+    def frames_of(length: int) -> int:
+        """Frames torch.stft(center=True, hop 128) yields for `length` samples (data_module.py:163-170)."""
+        return 1 + int(length) // 128
+
+    def stft_spec(self, wav: torch.Tensor, lengths, normalize: bool = True, spec_factor: float = 0.15,
+                  abs_exponent: float = 0.5, Tpad: Optional[int] = None):
+        """wav: fp32 CUDA [B, Lmax] (rows zero-padded to the longest utterance), lengths: samples per utterance.
+        Returns (Y complex64 [B,1,256,Tpad], peak fp32 [B]) - the padded model-domain spectrograms evaluate.py:107-115
+        builds per file, for the whole ragged batch at once."""
+        if wav.dtype != torch.float32 or not wav.is_cuda or wav.dim() != 2 or not wav.is_contiguous():
+            raise ValueError("wav must be a contiguous fp32 CUDA tensor [B, Lmax]")
+        B = wav.shape[0]
+        lens = [int(v) for v in lengths]
+        if len(lens) != B or max(lens) > wav.shape[1]:
+            raise ValueError("lengths must have one entry per row, each <= wav.shape[1]")
+        T = self.frames_of(max(lens))
+        if Tpad is None:
+            Tpad = ((T + 63) // 64) * 64
+        Y = torch.empty((B, 1, spec.IMAGE_SIZE, Tpad), dtype=torch.complex64, device=wav.device)
+        peak = torch.ones(B, dtype=torch.float32, device=wav.device)
+        arr = (C.c_int * B)(*lens)
+        self._check(self._lib.flowse_stft_spec(self._h, wav.data_ptr(), wav.stride(0), arr, B, int(normalize),
+                                               float(spec_factor), float(abs_exponent), Y.data_ptr(), Tpad,
+                                               peak.data_ptr(), _stream()))
+        return Y, peak
+
+    def spec_istft(self, X: torch.Tensor, lengths, peak: Optional[torch.Tensor] = None, spec_factor: float = 0.15,
+                   abs_exponent: float = 0.5) -> torch.Tensor:
+        """X: complex64 CUDA [B,1,256,Tpad] -> fp32 [B, max(lengths)] waveforms (VFModel.to_audio per row, times peak)."""
+        if X.dtype != torch.complex64 or not X.is_cuda or X.dim() != 4 or not X.is_contiguous():
+            raise ValueError("X must be a contiguous complex64 CUDA tensor [B,1,256,Tpad]")
+        B, Tpad = X.shape[0], X.shape[3]
+        lens = [int(v) for v in lengths]
+        if len(lens) != B:
+            raise ValueError("lengths must have one entry per batch element")
+        out = torch.empty((B, max(lens)), dtype=torch.float32, device=X.device)
+        arr = (C.c_int * B)(*lens)
+        self._check(self._lib.flowse_spec_istft(self._h, X.data_ptr(), Tpad, arr, B, float(spec_factor),
+                                                float(abs_exponent), _ptr(peak), out.data_ptr(), out.stride(0),
+                                                _stream()))
         return out
 
     def profile_forward(self):

@@ -144,6 +144,44 @@ class VFModel(nn.Module):
         sample = self.enhance_spec(Y.contiguous(), N=N, odesolver=odesolver, **kw)
         return self.to_audio(sample.squeeze(), T_orig) * norm
 
+    def _device_stft_ok(self):
+        dm = self.data_module
+        return dm.n_fft == 510 and dm.hop_length == 128 and dm.transform_type == "exponent"
+
+    def enhance_batch(self, wavs, N=5, odesolver="euler", normalize=True, **kw):
+        """evaluate.py:97-136 for a list of 1-D waveforms of ANY lengths on one CUDA device, without the per-file host
+        round trips: ONE batched device STFT (+ peak normalisation, amplitude compression, pad_spec) for all of them
+        (flowse_stft_spec), one sampler call per frame-count bucket (utterances whose padded T agree share a batch), one
+        batched device iSTFT (flowse_spec_istft).  Returns a list of enhanced waveforms, input order and lengths kept.
+        The prior noise is drawn per bucket in bucket order from torch's global generator of the device."""
+        if not wavs:
+            return []
+        if not self._device_stft_ok():
+            return [self.enhance(w.reshape(1, -1), N=N, odesolver=odesolver, **kw).reshape(-1) for w in wavs]
+        dev = wavs[0].device
+        ctx = self.flowse_context(dev)
+        dm = self.data_module
+        lens = [int(w.numel()) for w in wavs]
+        # bucket by padded frame count (pad_spec: multiples of 64), longest bucket first
+        buckets = {}
+        for i, L in enumerate(lens):
+            buckets.setdefault(((ctx.frames_of(L) + 63) // 64) * 64, []).append(i)
+        out = [None] * len(wavs)
+        for Tpad in sorted(buckets, reverse=True):
+            idx = buckets[Tpad]
+            Lb = [lens[i] for i in idx]
+            wav = torch.zeros((len(idx), max(Lb)), dtype=torch.float32, device=dev)
+            for r, i in enumerate(idx):
+                wav[r, :lens[i]] = wavs[i].reshape(-1).to(device=dev, dtype=torch.float32)
+            Y, peak = ctx.stft_spec(wav, Lb, normalize=normalize, spec_factor=dm.spec_factor,
+                                    abs_exponent=dm.spec_abs_exponent, Tpad=Tpad)
+            X = self.enhance_spec(Y, N=N, odesolver=odesolver, **kw)
+            x_hat = ctx.spec_istft(X.contiguous(), Lb, peak=peak if normalize else None, spec_factor=dm.spec_factor,
+                                   abs_exponent=dm.spec_abs_exponent)
+            for r, i in enumerate(idx):
+                out[i] = x_hat[r, :lens[i]]
+        return out
+
     # ---- STFT helpers (model.py:190-203) -----------------------------------------------------------------------
     def to_audio(self, spec, length=None):
         return self._istft(self._backward_transform(spec), length)

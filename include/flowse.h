@@ -77,8 +77,8 @@ int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const voi
 
 /* Options: "conv_impl" 0 = tcgen05 (default: halo kernel on high-resolution layers, per-tap kernel otherwise),
  * 1 = SIMT cross-check, 2 = per-tap kernel everywhere, 3 = like 0 with 3 rotating main accumulators in the halo kernel,
- * 4 = like 0 with the CTA-pair (cta_group::2) halo kernel; "graph" 0/1 = replay each NFE as a CUDA graph; "pdl" 0/1 = programmatic dependent launch between kernels
- * (process-wide, default 0: measured slower under graph replay). */
+ * 4 = like 0 with the CTA-pair (cta_group::2) halo kernel; "graph" 0/1 = replay each NFE as a CUDA graph; "pdl" = programmatic dependent launch (process-wide):
+ * 0 off, 1 every kernel, 2 (default) the low-resolution conv launches only - the fastest of the three under graph replay. */
 int flowse_set_option(flowse_ctx* ctx, const char* key, int value);
 
 /* Number of this library's kernel launches (graph kernel nodes included) since the context was created. */
@@ -95,6 +95,25 @@ int flowse_debug_tap(flowse_ctx* ctx, int module_idx, const float** ptr, int* C,
 
 /* Test hook: synchronous device-to-device copy (pairs with flowse_debug_tap). */
 int flowse_debug_copy(flowse_ctx* ctx, const void* src, void* dst, size_t bytes);
+
+/* ---- the step either side of the sampler: batched STFT / iSTFT + amplitude compression ---- */
+
+/* wav -> model-domain spectrogram for a ragged batch, no host synchronisation.  Replaces, per utterance,
+ *   y / y.abs().max()                                   (evaluate.py:109-110, when normalize != 0)
+ *   VFModel._stft = torch.stft(n_fft 510, hop 128, hann periodic, center=True)   (flowmse/data_module.py:163-170)
+ *   VFModel._forward_transform = |X|^e exp(j angle X) * spec_factor              (flowmse/data_module.py:149-162)
+ *   pad_spec: zero-pad the frame axis                                            (flowmse/util/other.py:83-90)
+ * wav: DEVICE fp32 [B][wav_stride]; lengths_host: HOST int [B] samples per utterance (>= 256);
+ * Y: DEVICE complex [B,1,256,Tpad], Tpad >= 1 + max(len)/128 (frames beyond an utterance's own count are zero);
+ * peak_out: DEVICE fp32 [B], receives max|wav| per utterance (required when normalize != 0). */
+int flowse_stft_spec(flowse_ctx* ctx, const float* wav, long long wav_stride, const int* lengths_host, int B, int normalize,
+                     float spec_factor, float abs_exponent, void* Y, int Tpad, float* peak_out, void* stream);
+
+/* Model-domain spectrogram -> wav.  Replaces VFModel.to_audio = istft(_backward_transform(spec), length)
+ * (flowmse/model.py:190-203, data_module.py:164-175) and the `* norm_factor` of evaluate.py:134-135 (peak may be NULL).
+ * X: DEVICE complex [B,1,256,Tpad]; wav_out: DEVICE fp32 [B][wav_stride], zero beyond each utterance's length. */
+int flowse_spec_istft(flowse_ctx* ctx, const void* X, int Tpad, const int* lengths_host, int B, float spec_factor,
+                      float abs_exponent, const float* peak, float* wav_out, long long wav_stride, void* stream);
 
 /* ---- op-level entry points (used by the parity tests; same kernels as the path above) ---- */
 

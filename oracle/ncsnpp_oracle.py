@@ -330,3 +330,25 @@ def pad_spec(Y: torch.Tensor) -> torch.Tensor:
     T = Y.size(3)
     num_pad = 64 - T % 64 if T % 64 != 0 else 0
     return F.pad(Y, (0, num_pad, 0, 0))
+
+
+# ----------------------------------------------------------------------------
+# STFT / iSTFT either side of the sampler
+# ----------------------------------------------------------------------------
+def stft_spec(wav: torch.Tensor, normalize: bool = True, spec_factor: float = 0.15, e: float = 0.5):
+    """evaluate.py:109-115 for one utterance [1, L]: peak-normalise, SpecsDataModule.stft (data_module.py:163-170),
+    spec_fwd (data_module.py:149-162), pad_spec (util/other.py:83-90).  Returns (Y [1,1,256,Tpad], peak)."""
+    peak = wav.abs().max() if normalize else torch.tensor(1.0)
+    win = torch.hann_window(510, periodic=True)
+    S = torch.stft(wav / peak, n_fft=510, hop_length=128, window=win, center=True, return_complex=True)
+    S = S.abs() ** e * torch.exp(1j * S.angle()) * spec_factor
+    return pad_spec(S.unsqueeze(0)), peak
+
+
+def spec_istft(X: torch.Tensor, length: int, peak=1.0, spec_factor: float = 0.15, e: float = 0.5) -> torch.Tensor:
+    """VFModel.to_audio (model.py:190-203): spec_back (data_module.py:164-175) then torch.istft(..., length), times the
+    peak (evaluate.py:134-135).  X: [1,1,256,T] or [256,T]."""
+    S = X.squeeze() / spec_factor
+    S = S.abs() ** (1 / e) * torch.exp(1j * S.angle())
+    win = torch.hann_window(510, periodic=True)
+    return torch.istft(S, n_fft=510, hop_length=128, window=win, center=True, length=length) * peak

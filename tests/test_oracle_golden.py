@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import ncsnpp_oracle as orc
@@ -52,3 +53,16 @@ def test_pad_spec():
     y = torch.zeros(1, 1, 256, 501, dtype=torch.complex64)
     assert orc.pad_spec(y).shape[-1] == 512
     assert orc.pad_spec(orc.pad_spec(y)).shape[-1] == 512
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_oracle_stft_istft_match_reference_golden(golden_dir, name):
+    """oracle.stft_spec / spec_istft vs the vectors the reference's SpecsDataModule produced (gen_golden_stft.py)."""
+    g = np.load(os.path.join(golden_dir, "stft_roundtrip.npz"))
+    wav = torch.from_numpy(g[f"wav_{name}"])
+    Y, peak = orc.stft_spec(wav)
+    assert torch.equal(torch.view_as_real(Y), torch.from_numpy(g[f"Y_{name}"]))
+    assert float(peak) == float(g[f"norm_{name}"][0])
+    X = torch.view_as_complex(torch.from_numpy(g[f"X_{name}"]).contiguous())
+    xh = orc.spec_istft(X, wav.shape[1], peak)
+    assert torch.allclose(xh, torch.from_numpy(g[f"xhat_{name}"]), rtol=0, atol=1e-7)
