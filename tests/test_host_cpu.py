@@ -212,3 +212,47 @@ def test_config1_stft_plumbing_matches_reference_golden(golden_dir):
     # round trip of the transform pair and of the STFT pair (to_audio path, model.py:190-203)
     back = st.istft(st.spec_back(st.spec_fwd(st.stft(wav))), length=n)
     assert torch.allclose(back, wav, atol=2e-4)
+
+
+# ---- evaluate driver: host logic ---------------------------------------------------------------
+def test_evaluate_cli_matches_reference_arguments():
+    """Same argument names / defaults as /root/reference/evaluate.py:27-43."""
+    from flowmse_b200.evaluate import build_parser
+    a = build_parser().parse_args(["--folder_destination", "/tmp/x", "--test_dir", "/data"])
+    assert (a.odesolver_type, a.odesolver, a.reverse_starting_point, a.last_eval_point, a.N, a.N_mid) == \
+           ("white", "euler", 1.0, 0.03, 5, 0)
+    assert a.ckpt is None and a.test_dir == "/data"
+
+
+def test_evaluate_batches_and_metrics(tmp_path):
+    from flowmse_b200 import evaluate as ev
+    # frames / padded frames as torch.stft(center=True, hop 128) + pad_spec give them
+    assert ev.frames_of(64000) == 501 and ev.padded_frames(64000) == 512
+    assert ev.padded_frames(128 * 63) == 64 and ev.padded_frames(128 * 64) == 128
+    n = [64000, 64000, 9000, 30000, 64000, 9100]
+    batches = ev.make_batches(range(len(n)), n, max_batch_frames=1024)
+    flat = sorted(i for b in batches for i in b)
+    assert flat == list(range(len(n)))
+    for b in batches:
+        assert len({ev.padded_frames(n[i]) for i in b}) == 1
+        assert len(b) == 1 or sum(ev.padded_frames(n[i]) for i in b) <= 1024
+    assert batches[0] == [0, 1]                      # longest bucket first, two 512-frame utterances per batch
+    # SI-SDR family (utils.py:10-36) on a hand-computable case: orthogonal target / noise / artefact directions
+    s = np.zeros(8); s[0] = 1.0
+    noise = np.zeros(8); noise[1] = 1.0
+    art = np.zeros(8); art[2] = 0.1
+    sdr, sir, sar = ev.energy_ratios(2.0 * s + 0.5 * noise + art, s, noise)
+    assert abs(sdr - 10 * np.log10(4 / 0.26)) < 1e-9 and abs(sir - 10 * np.log10(4 / 0.25)) < 1e-9
+    assert abs(sar - 10 * np.log10(4 / 0.01)) < 1e-9
+    rng = np.random.RandomState(0)
+    s, noise = rng.standard_normal(16000), 0.1 * rng.standard_normal(16000)
+    m = ev.file_metrics(s.astype(np.float32), (s + noise).astype(np.float32), (s + 0.01 * noise).astype(np.float32))
+    assert set(m) == {"pesq", "estoi", "si_sdr", "si_sir", "si_sar"} and m["si_sdr"] > 35
+    # wav round trip at 16 bit
+    x = (0.5 * np.sin(np.arange(4000) * 0.01)).astype(np.float32)
+    ev.write_wav(str(tmp_path / "a.wav"), x)
+    assert np.abs(ev.read_wav(str(tmp_path / "a.wav")) - x).max() <= 1.0 / 32768
+    # synthetic VoiceBank-DEMAND-shaped set: deterministic, durations inside [1, 10] s
+    a, b = ev.synthetic_test_set(6), ev.synthetic_test_set(6)
+    assert all(np.array_equal(p[2], q[2]) for p, q in zip(a, b))
+    assert all(16000 <= len(p[2]) <= 160000 for p in a)
