@@ -137,9 +137,16 @@ __device__ __forceinline__ void cluster_reduce_rows(const GemmParams& p, const C
     rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (o[i] >= 0) {
       if (p.residual) rr[i] = __ldg(reinterpret_cast<const float4*>(p.residual + o[i]));
-      const uint32_t local = red0 + static_cast<uint32_t>((r * RED_STRIDE + 4 * c4) * 4);
+      if (p.partial) {
+        // partial planes in global memory (L2-resident): an SM reads L2 several times faster than a peer's shared memory
 #pragma unroll
-      for (int zz = 0; zz < S; ++zz) pv[i][zz] = ld_dsmem_f4(map_to_cta(local, static_cast<uint32_t>(zz)));
+        for (int zz = 0; zz < S; ++zz)
+          pv[i][zz] = __ldcg(reinterpret_cast<const float4*>(p.partial + zz * p.partial_plane + o[i]));
+      } else {
+        const uint32_t local = red0 + static_cast<uint32_t>((r * RED_STRIDE + 4 * c4) * 4);
+#pragma unroll
+        for (int zz = 0; zz < S; ++zz) pv[i][zz] = ld_dsmem_f4(map_to_cta(local, static_cast<uint32_t>(zz)));
+      }
     }
   }
 #pragma unroll
@@ -347,8 +354,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
         for (int j = 0; j < CH; ++j)
           r[j] = __float_as_uint((__uint_as_float(r[j]) + __uint_as_float(r2[j])) + __uint_as_float(r3[j]));
-        if (p.cluster_s > 1) {
-          // cluster reduction: park the raw tile (row = TMEM lane) in the now idle operand stages
+        if (p.cluster_s > 1 && !p.partial) {
+          // cluster reduction through DSMEM: park the raw tile (row = TMEM lane) in the now idle operand stages
           float* red = reinterpret_cast<float*>(smem_raw + (smem_base - ptx::smem_u32(smem_raw))) +
                        (q * 32 + lane) * C::RED_STRIDE + col_base + c0;
 #pragma unroll
@@ -455,7 +462,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
     __syncwarp();
-    cluster_sync_all();                                    // no CTA's shared memory goes away while a peer still reads it
+    if (!p.partial) cluster_sync_all();                    // no CTA's shared memory goes away while a peer still reads it
   }
 
   if (threadIdx.x == 64) stamp(4);
@@ -731,12 +738,21 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   // Cluster reduction: the S CTAs of a tile become one cluster (1,1,S) and reduce through distributed shared memory.
   // S is capped by the cluster size the device can co-schedule with this kernel's shared-memory footprint (16 is a
   // non-portable size; 8 is always available).  FLOWSE_SPLITK=2pass keeps the partial-plane + reduce-kernel path.
+  // Two ways for the cluster to exchange its partial tiles: "dsmem" (default) parks them in shared memory and reads the
+  // peers' copies (ld.shared::cluster); "l2" writes them to the L2-resident scratch planes and reads those back after the
+  // cluster barrier.  Measured on B200 (tools/dbg_conv.py, grid (4,2,8), K = 2304): dsmem parks in 1.5 us and reduces in
+  // 4.0 us (distributed shared memory moves ~20 B/cycle/SM), l2 parks in 3.6 us and reduces in 2.0 us - the same 5.5 us;
+  // end to end dsmem is 0.5 % faster (22.84 vs 22.96 ms per sampler call) and needs no scratch.  Both beat the
+  // two-pass path (FLOWSE_SPLITK=2pass: partial planes + splitk_reduce_kernel, 23.28 ms).
   static const int splitk_mode = [] {
     const char* e = getenv("FLOWSE_SPLITK");
-    return (e && !strcmp(e, "2pass")) ? 0 : 1;
+    if (e && !strcmp(e, "2pass")) return 0;
+    if (e && !strcmp(e, "dsmem")) return 1;
+    if (e && !strcmp(e, "l2")) return 2;
+    return 1;
   }();
   bool cluster_reduce = false;
-  if (splitk_mode == 1 && tiles <= 74 && nkb_total >= 8) {
+  if (splitk_mode >= 1 && tiles <= 74 && nkb_total >= 8) {
     const int max_cluster = (tiles <= max_clusters16<BN>()) ? 16 : 8;
     int Sc = std::min(std::min(148 / tiles, nkb_total / 4), max_cluster);
     while (Sc & (Sc - 1)) Sc &= Sc - 1;                  // cluster sizes: powers of two
@@ -744,6 +760,11 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
       cluster_reduce = true;
       S = Sc;
       p.ksplit = S; p.cluster_s = S; p.partial = nullptr; p.partial_plane = 0; grid.z = S;
+      const long long plane = static_cast<long long>(a.B) * a.H * a.W * a.ldc;
+      if (splitk_mode == 2 && a.splitk_scratch && a.ldc == a.Cout &&
+          static_cast<size_t>(S) * plane <= a.splitk_scratch_elems) {
+        p.partial = a.splitk_scratch; p.partial_plane = plane;
+      }
     }
   }
   static const bool dbg = getenv("FLOWSE_CONV_DBG") != nullptr;

@@ -32,7 +32,8 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_mode() == 1 ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed =
+      (pdl_mode() == 1 || (pdl_mode() == 3 && static_cast<size_t>(grid.x) * grid.y * grid.z <= 148)) ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   ++launch_counter();
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

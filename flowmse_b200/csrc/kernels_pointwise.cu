@@ -17,7 +17,7 @@ int& pdl_mode() {
   // mode 0 23.39 / 23.14 ms, mode 2 23.00 / 23.03 ms, mode 1 24.26 / 24.05 ms per sampler call - with every kernel
   // opted in, early-scheduled CTAs of the next kernel compete with the running persistent kernels.  Default 2;
   // FLOWSE_PDL=<mode> / option "pdl" select another.
-  static int mode = [] { const char* e = getenv("FLOWSE_PDL"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }();
+  static int mode = [] { const char* e = getenv("FLOWSE_PDL"); return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2; }();
   return mode;
 }
 
