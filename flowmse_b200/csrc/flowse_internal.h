@@ -92,15 +92,14 @@ void launch_fir_down4(const float4* in, float4* out, int B, int H, int W, cudaSt
 // Combine(method='sum') (layerspp.py:52-57): out = h + conv1x1(4->C)(pyr) + b
 void launch_combine(const float* h, const float4* pyr, const float* w /*[C][4]*/, const float* b, float* out,
                     double* qstats /*quad statistics of the output, zeroed*/, int B, int H, int W, int C, cudaStream_t s);
-// pyramid = FIR-up(prev) + head (ncsnpp.py:357-363). prev may be null (deepest level). head ld = 4.
-void launch_pyr_accum(const float4* prev /*[B,H/2,W/2,4]*/, const float4* head, float4* out, int B, int H, int W,
-                      cudaStream_t s);
 // d = output_layer(pyr / t) (ncsnpp.py:398-403).
 //   mode 0: out = d                         (NCSNpp.forward result)
 //   mode 1: out = -d                        (VFModel.forward result, model.py:164-170)
 //   mode 2: out = xin + stepsize * d        (fused Euler update: x + (-d) * (-stepsize))
 void launch_final(const float4* pyr, const float* t /*[B]*/, const float* wo /*[2][4]*/, const float* bo /*[2]*/,
                   const float2* xin, const float* stepsize_dev, float2* out, int mode, int B, int HW, cudaStream_t s);
+// busy-wait `ns` nanoseconds on the stream (measurement helper, not counted as a library launch)
+void launch_spin(unsigned long long ns, cudaStream_t s);
 // row softmax in place, rows x cols fp32
 void launch_softmax_rows(float* s, int rows, int cols, cudaStream_t st);
 
@@ -188,8 +187,12 @@ struct SgemmArgs {
   const float* residual; int ldr; long long strideR;   // optional, added after bias
   int div_sqrt2;
   __half* split_out;                               // optional: also not used (reserved)
+  // optional: accumulate the quad statistics of C (layout above, zeroed buffer) in the epilogue.  Rows are grouped into
+  // batch elements of qs_rows_per_batch rows; needs batch == 1, N % 4 == 0 and qs_rows_per_batch % sgemm_tile_rows() == 0.
+  double* qstats; int qs_rows_per_batch;
 };
 void launch_sgemm(const SgemmArgs& a, cudaStream_t s);
+int sgemm_tile_rows(const SgemmArgs& a);           // M tile the launcher will pick (64 or 32)
 
 // ---------------------------------------------------------------------------------------------
 // Batched STFT / iSTFT + amplitude compression (stft.cu); n_fft 510, hop 128, hann, center=True

@@ -378,7 +378,7 @@ gn_prep_resample_kernel(const PrepK k) {
 
 // ---------------------------------------------------------------------------------------------
 // Pyramid head, fully fused: pyr = FIR-up(prev) + conv3x3(C -> 4)(SiLU(GN(h))) + bias
-// (/root/reference/flowmse/backbones/ncsnpp.py:347-366; FIR closed form as in pyr_accum).
+// (/root/reference/flowmse/backbones/ncsnpp.py:347-366; FIR-up closed form of SURVEY.md Appendix B).
 // Cout = 4 is the wrong shape for the tensor cores (a 128 x 16 MMA tile is 3/4 padding and still needs the
 // fp16 hi/lo operand pass over h); here ONE kernel reads h (fp32) once, normalises + activates it into a shared-memory
 // halo tile, and evaluates the 4 outputs with exact fp32 FMAs.  Output tile (RG*P) x TW pixels; a thread owns P vertically
@@ -537,7 +537,7 @@ head_conv_kernel(const HeadK k) {
     }
     v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
     if (k.prev) {
-      // StyleGAN2 FIR upsample x2 of the coarser pyramid (taps {1,3,3,9}/16), same arithmetic as pyr_accum
+      // StyleGAN2 FIR upsample x2 of the coarser pyramid: 2-D taps {1,3,3,9}/16, zero boundary (up_or_down_sampling.py:195-224)
       const int Hp = k.H >> 1, Wp = k.W >> 1;
       const int mh = h >> 1, mw = w >> 1;
       const int h_a = (h & 1) ? mh : mh - 1, h_b = (h & 1) ? mh + 1 : mh;

@@ -342,46 +342,6 @@ combine_kernel(const float* __restrict__ h, const float4* __restrict__ pyr, cons
   }
 }
 
-// out = FIR-up(prev) + head                           (ncsnpp.py:357-363)
-__global__ void __launch_bounds__(256)
-pyr_accum_kernel(const float4* __restrict__ prev, const float4* __restrict__ head, float4* __restrict__ out, int B,
-                 int H, int W) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const size_t total = static_cast<size_t>(B) * H * W;
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  float4 acc = head[i];
-  if (prev) {
-    const int w = i % W;
-    const int h = (i / W) % H;
-    const int b = i / (static_cast<size_t>(W) * H);
-    const int Hp = H >> 1, Wp = W >> 1;
-    const int mh = h >> 1, mw = w >> 1;
-    const int h_a = (h & 1) ? mh : mh - 1, h_b = (h & 1) ? mh + 1 : mh;
-    const float wha = (h & 1) ? 3.f : 1.f, whb = (h & 1) ? 1.f : 3.f;
-    const int w_a = (w & 1) ? mw : mw - 1, w_b = (w & 1) ? mw + 1 : mw;
-    const float wwa = (w & 1) ? 3.f : 1.f, wwb = (w & 1) ? 1.f : 3.f;
-    float4 up = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int hi = a ? h_b : h_a;
-      if (hi < 0 || hi >= Hp) continue;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int wi = c ? w_b : w_a;
-        if (wi < 0 || wi >= Wp) continue;
-        const float wgt = (a ? whb : wha) * (c ? wwb : wwa) * (1.f / 16.f);
-        const float4 v = __ldg(prev + (static_cast<size_t>(b) * Hp + hi) * Wp + wi);
-        up.x = fmaf(wgt, v.x, up.x); up.y = fmaf(wgt, v.y, up.y);
-        up.z = fmaf(wgt, v.z, up.z); up.w = fmaf(wgt, v.w, up.w);
-      }
-    }
-    acc.x = up.x + acc.x; acc.y = up.y + acc.y; acc.z = up.z + acc.z; acc.w = up.w + acc.w;
-  }
-  out[i] = acc;
-}
-
 // d = output_layer(pyr / t); see launch_final for the modes
 __global__ void __launch_bounds__(256)
 final_kernel(const float4* __restrict__ pyr, const float* __restrict__ t, const float* __restrict__ wo,
@@ -486,10 +446,18 @@ void launch_combine(const float* h, const float4* pyr, const float* w, const flo
   launch_k(combine_kernel, grid, dim3(256), 0, s, h, pyr, w, b, out, qstats, npix, C);
 }
 
-void launch_pyr_accum(const float4* prev, const float4* head, float4* out, int B, int H, int W, cudaStream_t s) {
-  const size_t total = static_cast<size_t>(B) * H * W;
-  launch_k(pyr_accum_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, prev, head, out, B, H, W);
+// Holds the stream for `ns` nanoseconds: flowse_profile_forward queues a whole evaluation behind it so that the per-op
+// events time kernels running back to back, not the host's launch cadence.
+__global__ void spin_kernel(unsigned long long ns) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 >= ns) break;
+  }
 }
+void launch_spin(unsigned long long ns, cudaStream_t s) { spin_kernel<<<1, 1, 0, s>>>(ns); }
 
 void launch_final(const float4* pyr, const float* t, const float* wo, const float* bo, const float2* xin,
                   const float* stepsize_dev, float2* out, int mode, int B, int HW, cudaStream_t s) {

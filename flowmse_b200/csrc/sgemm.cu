@@ -155,6 +155,7 @@ sgemm_kernel(const SgemmArgs a) {
   }
   const bool vecC = (a.ldc % 4 == 0) && ((reinterpret_cast<size_t>(C) & 15) == 0) &&
                     (!R || ((a.ldr % 4 == 0) && ((reinterpret_cast<size_t>(R) & 15) == 0)));
+  float qs_s = 0.f, qs_q = 0.f;                      // this thread's share of the quad statistics (its 4 columns = one quad)
 #pragma unroll
   for (int i = 0; i < RM; ++i) {
     const int m = m0 + ty * RM + i;
@@ -175,14 +176,38 @@ sgemm_kernel(const SgemmArgs a) {
     else
 #pragma unroll
       for (int j = 0; j < 4; ++j) if (n + j < a.N) dst[j] = v[j];
+    if (n + 3 < a.N) {
+      qs_s += (v[0] + v[1]) + (v[2] + v[3]);
+      qs_q += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+    }
+  }
+  if (a.qstats) {
+    // the tile's rows belong to one batch element (launcher contract): fold the 16 row groups in fixed order, then one
+    // fp64 atomic pair per quad into the replica keyed by the row-tile index
+    float (*s_q)[16][2] = reinterpret_cast<float (*)[16][2]>(&sA[0][0]);     // the K loop has ended with a barrier
+    s_q[ty][tx][0] = qs_s; s_q[ty][tx][1] = qs_q;
+    __syncthreads();
+    if (ty == 0 && n0 + tx * 4 + 3 < a.N) {
+      float as = 0.f, aq = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) { as += s_q[g][tx][0]; aq += s_q[g][tx][1]; }
+      const int b = m0 / a.qs_rows_per_batch;
+      double* dst = qstat_slot(a.qstats, b, blockIdx.y, a.N >> 2) + static_cast<size_t>((n0 >> 2) + tx) * 2;
+      atomicAdd(dst, static_cast<double>(as));
+      atomicAdd(dst + 1, static_cast<double>(aq));
+    }
   }
 }
 
 }  // namespace
 
-void launch_sgemm(const SgemmArgs& a, cudaStream_t s) {
+int sgemm_tile_rows(const SgemmArgs& a) {
   const long long tiles64 = static_cast<long long>((a.N + TN - 1) / TN) * ((a.M + 63) / 64) * a.batch;
-  if (tiles64 >= 120 && a.M > 32) {
+  return (tiles64 >= 120 && a.M > 32) ? 64 : 32;
+}
+
+void launch_sgemm(const SgemmArgs& a, cudaStream_t s) {
+  if (sgemm_tile_rows(a) == 64) {
     dim3 grid((a.N + TN - 1) / TN, (a.M + 63) / 64, a.batch);
     launch_k(sgemm_kernel<64>, grid, dim3(256), 0, s, a);
   } else {
