@@ -118,7 +118,8 @@ struct HeadW { int c = 0; float *gn_g = nullptr, *gn_b = nullptr, *bias = nullpt
 
 struct Act { float* p = nullptr; int C = 0, H = 0, W = 0; double* qs = nullptr; };   // qs: quad statistics [B][C/4][2]
 
-// kind: 0 misc, 1 gn_stats, 2 gn_prep, 3 conv_gemm, 4 attention, 5 small 4-channel / input kernels, 6 time embedding
+// kind: 0 misc, 1 gn_stats, 2 gn_prep, 3 conv_gemm (per-tap kernel), 4 attention, 5 small 4-channel / input kernels,
+//       6 time embedding, 7 conv_halo (halo kernel; chosen at plan time with the conv_impl option in force)
 struct Op { std::function<int(cudaStream_t)> fn; int nk; int kind; double flops; int info[4]; };
 
 struct Plan {
@@ -333,12 +334,17 @@ struct Arena {
 // conv_impl: 0 = auto (halo kernel for the high-resolution layers, per-tap kernel otherwise), 1 = SIMT cross-check,
 // 2 = per-tap tcgen05 kernel everywhere, 3 = auto with 3 rotating main accumulators in the halo kernel,
 // 4 = auto with the CTA-pair (cta_group::2) halo kernel.
+// the halo kernel takes the layers with at least ~2/3 of a wave of its 16 x 8 pixel x 128 channel tiles
+bool conv_uses_halo(const flowse_ctx* ctx, const ConvGemmArgs& a) {
+  return ctx->conv_impl != 1 && ctx->conv_impl != 2 && conv_halo_supported(a) &&
+         static_cast<long long>(a.B) * (a.H / 16) * (a.W / 8) * ((a.Cout + 127) / 128) >= 100;
+}
+
 int run_conv(flowse_ctx* ctx, const ConvGemmArgs& a, cudaStream_t s) {
   std::string e;
   int rc;
   if (ctx->conv_impl == 1) rc = launch_conv_gemm_simt(a, s, &e);
-  else if (ctx->conv_impl != 2 && conv_halo_supported(a) &&
-           static_cast<long long>(a.B) * (a.H / 16) * (a.W / 8) * ((a.Cout + 127) / 128) >= 100)
+  else if (conv_uses_halo(ctx, a))
     rc = launch_conv_halo(a, ctx->conv_impl == 3 ? 3 : (ctx->conv_impl == 4 ? 2 : 1), s, &e);
   else rc = launch_conv_gemm(a, s, &e);
   if (rc) ctx->err = e;
@@ -400,7 +406,7 @@ struct Builder {
     c0.residual = nullptr; c0.div_sqrt2 = 0; c0.out = scrH1; c0.Cout = r.cout; c0.ldc = r.cout;
     c0.B = B; c0.H = Ho; c0.W = Wo;
     c0.splitk_scratch = splitk; c0.splitk_scratch_elems = kSplitKScratchElems; c0.qstats = st1;
-    { flowse_ctx* cx = ctx; push(2, [=](cudaStream_t s) { return run_conv(cx, c0, s); }, 3, conv_flops(c0), c0.H, c0.W, c0.ntaps * c0.Cin + (c0.X ? c0.Cin2 : 0), c0.Cout); }
+    { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c0, s); }, conv_uses_halo(cx, c0) ? 7 : 3, conv_flops(c0), c0.H, c0.W, c0.ntaps * c0.Cin + (c0.X ? c0.Cin2 : 0), c0.Cout); }
     float* h1 = scrH1; const int Co = r.cout;
     PrepArgs pb{};
     pb.src1 = h1; pb.C1 = Co; pb.src2 = nullptr; pb.C2 = 0; pb.qs1 = st1; pb.gamma = r.gn1_g; pb.beta = r.gn1_b;
@@ -412,7 +418,7 @@ struct Builder {
     c1.bias_bstride = 0; c1.residual = r.has_sc ? nullptr : s1; c1.div_sqrt2 = 1; c1.out = out.p; c1.Cout = Co;
     c1.ldc = Co; c1.B = B; c1.H = Ho; c1.W = Wo;
     c1.splitk_scratch = splitk; c1.splitk_scratch_elems = kSplitKScratchElems; c1.qstats = out.qs;
-    { flowse_ctx* cx = ctx; push(2, [=](cudaStream_t s) { return run_conv(cx, c1, s); }, 3, conv_flops(c1), c1.H, c1.W, c1.ntaps * c1.Cin + (c1.X ? c1.Cin2 : 0), c1.Cout); }
+    { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c1, s); }, conv_uses_halo(cx, c1) ? 7 : 3, conv_flops(c1), c1.H, c1.W, c1.ntaps * c1.Cin + (c1.X ? c1.Cin2 : 0), c1.Cout); }
     plan->taps[mi] = out;
     return out;
   }

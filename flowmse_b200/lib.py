@@ -256,7 +256,7 @@ class Context:
         n = C.c_int()
         self._check(self._lib.flowse_profile_forward(self._h, n_max, kinds.ctypes.data, ms.ctypes.data,
                                                      flops.ctypes.data, info.ctypes.data, C.byref(n)))
-        names = ["misc", "gn_stats", "gn_prep", "conv_gemm", "attention", "small", "temb"]
+        names = ["misc", "gn_stats", "gn_prep", "conv_gemm", "attention", "small", "temb", "conv_halo"]
         return [dict(kind=names[kinds[k]], ms=float(ms[k]), flops=float(flops[k]), H=int(info[4 * k]),
                      W=int(info[4 * k + 1]), K=int(info[4 * k + 2]), Cout=int(info[4 * k + 3])) for k in range(n.value)]
 

@@ -85,8 +85,9 @@ int flowse_set_option(flowse_ctx* ctx, const char* key, int value);
 long long flowse_kernel_launches(const flowse_ctx* ctx);
 
 /* Measurement hook: run ONE network evaluation of the current plan op by op on a private stream with a CUDA event
- * after every op.  Per op: kind (0 misc, 1 gn_stats, 2 gn_prep, 3 conv_gemm, 4 attention, 5 small, 6 temb), elapsed ms,
- * algorithmic FLOPs (conv_gemm only) and info = {H, W, K, Cout} (conv_gemm only). */
+ * after every op (the evaluation is queued behind a spin kernel so the kernels run back to back).  Per op: kind (0 misc,
+ * 1 gn_stats, 2 gn_prep, 3 conv_gemm = per-tap conv kernel, 4 attention, 5 small, 6 temb, 7 conv_halo = halo conv kernel),
+ * elapsed ms, algorithmic FLOPs and info = {H, W, K, Cout} (convs and pyramid heads only). */
 int flowse_profile_forward(flowse_ctx* ctx, int max_ops, int* kinds, float* ms, double* flops, int* info, int* n_ops);
 
 /* Test hook: device pointer / shape (NHWC fp32) of the output of all_modules[module_idx] from the last forward of
