@@ -112,34 +112,57 @@ temb_mlp_kernel(const TembWeights w, const float* __restrict__ t, float* __restr
     emb[128 + j] = cosf(xp);
   }
   __syncthreads();
-  // one warp per output row, lanes stride over the inputs (coalesced weight reads), 16 warps x 32 rows each
+  // one warp per output row, lanes stride over the inputs (coalesced weight reads), 16 warps x 32 rows each.  The kernel
+  // is a single latency chain (one CTA per batch element), so a warp requests the weights of RB = 8 rows before it
+  // consumes the first (RB2 = 4 rows for the 512-wide second layer: register budget): 4 / 8 instead of 32 dependent
+  // global round trips per layer.
   const int warp = j >> 5, lane = j & 31;
-  for (int r = warp; r < 512; r += 16) {
-    const float4* row = reinterpret_cast<const float4*>(w.l1_w + static_cast<size_t>(r) * 256);
-    float acc = 0.f;
+  constexpr int RB = 8;
+  for (int r0 = warp * RB; r0 < 512; r0 += 16 * RB) {
+    float4 wv[RB][2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float4 wv = __ldg(row + lane + 32 * i);
-      const float4 x = *reinterpret_cast<const float4*>(&emb[4 * (lane + 32 * i)]);
-      acc = fmaf(wv.x, x.x, acc); acc = fmaf(wv.y, x.y, acc); acc = fmaf(wv.z, x.z, acc); acc = fmaf(wv.w, x.w, acc);
+    for (int k = 0; k < RB; ++k) {
+      const float4* row = reinterpret_cast<const float4*>(w.l1_w + static_cast<size_t>(r0 + k) * 256);
+      wv[k][0] = __ldg(row + lane); wv[k][1] = __ldg(row + lane + 32);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) h1[r] = silu_f(acc + w.l1_b[r]);
+    for (int k = 0; k < RB; ++k) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float4 x = *reinterpret_cast<const float4*>(&emb[4 * (lane + 32 * i)]);
+        acc = fmaf(wv[k][i].x, x.x, acc); acc = fmaf(wv[k][i].y, x.y, acc);
+        acc = fmaf(wv[k][i].z, x.z, acc); acc = fmaf(wv[k][i].w, x.w, acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) h1[r0 + k] = silu_f(acc + w.l1_b[r0 + k]);
+    }
   }
   __syncthreads();
-  for (int r = warp; r < 512; r += 16) {
-    const float4* row = reinterpret_cast<const float4*>(w.l2_w + static_cast<size_t>(r) * 512);
-    float acc = 0.f;
+  constexpr int RB2 = 4;
+  for (int r0 = warp * RB2; r0 < 512; r0 += 16 * RB2) {
+    float4 wv[RB2][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 wv = __ldg(row + lane + 32 * i);
-      const float4 x = *reinterpret_cast<const float4*>(&h1[4 * (lane + 32 * i)]);
-      acc = fmaf(wv.x, x.x, acc); acc = fmaf(wv.y, x.y, acc); acc = fmaf(wv.z, x.z, acc); acc = fmaf(wv.w, x.w, acc);
+    for (int k = 0; k < RB2; ++k) {
+      const float4* row = reinterpret_cast<const float4*>(w.l2_w + static_cast<size_t>(r0 + k) * 512);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wv[k][i] = __ldg(row + lane + 32 * i);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) temb_act[static_cast<size_t>(b) * 512 + r] = silu_f(acc + w.l2_b[r]);   // act(temb), input of every Dense_0
+    for (int k = 0; k < RB2; ++k) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 x = *reinterpret_cast<const float4*>(&h1[4 * (lane + 32 * i)]);
+        acc = fmaf(wv[k][i].x, x.x, acc); acc = fmaf(wv[k][i].y, x.y, acc);
+        acc = fmaf(wv[k][i].z, x.z, acc); acc = fmaf(wv[k][i].w, x.w, acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      // act(temb), input of every Dense_0
+      if (lane == 0) temb_act[static_cast<size_t>(b) * 512 + r0 + k] = silu_f(acc + w.l2_b[r0 + k]);
+    }
   }
 }
 

@@ -8,6 +8,10 @@ loaders) is out of scope.
 """
 from __future__ import annotations
 
+import contextlib
+import sys
+import types
+
 import torch
 import torch.nn as nn
 
@@ -63,6 +67,42 @@ class SpecTransform:
         return spec
 
 
+@contextlib.contextmanager
+def reference_pickle_shims():
+    """Lightning checkpoints written by the reference pickle ``hyper_parameters['data_module_cls']`` BY REFERENCE as
+    ``flowmse.data_module.SpecsDataModule`` (VFModel.__init__ keeps the class, model.py:34-56, and
+    ``save_hyperparameters`` stores it), so ``torch.load`` must be able to import that name.  Where the reference package
+    (or one of its training-only dependencies: pytorch_lightning, torch_ema) is not importable, placeholder modules are
+    installed for the duration of the load; the class is never instantiated here (SpecTransform replaces it)."""
+    created = []
+    try:
+        import flowmse.data_module  # noqa: F401  (the real package is importable: nothing to do)
+    except Exception:
+        pkg = sys.modules.get("flowmse")
+        if pkg is None:
+            pkg = types.ModuleType("flowmse")
+            pkg.__path__ = []
+            sys.modules["flowmse"] = pkg
+            created.append("flowmse")
+        if "flowmse.data_module" not in sys.modules:
+            dm = types.ModuleType("flowmse.data_module")
+
+            class SpecsDataModule:       # placeholder for unpickling only
+                pass
+
+            SpecsDataModule.__module__ = "flowmse.data_module"
+            SpecsDataModule.__qualname__ = "SpecsDataModule"
+            dm.SpecsDataModule = SpecsDataModule
+            sys.modules["flowmse.data_module"] = dm
+            pkg.data_module = dm
+            created.append("flowmse.data_module")
+    try:
+        yield
+    finally:
+        for name in created:
+            sys.modules.pop(name, None)
+
+
 class VFModel(nn.Module):
     _flowse_fused = True
 
@@ -82,8 +122,9 @@ class VFModel(nn.Module):
     def load_from_checkpoint(cls, checkpoint_path, map_location="cpu", **override):
         """Read a reference checkpoint (Lightning 1.6.5 + torch_ema 0.3 layout, model.py:81-90)."""
         try:
-            ck = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
-        except Exception as e:   # the pickled data_module_cls needs flowmse.data_module importable
+            with reference_pickle_shims():
+                ck = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        except Exception as e:
             raise RuntimeError(f"cannot unpickle {checkpoint_path}: {e}") from e
         return cls.from_checkpoint_dict(ck, **override)
 

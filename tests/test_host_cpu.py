@@ -256,3 +256,31 @@ def test_evaluate_batches_and_metrics(tmp_path):
     a, b = ev.synthetic_test_set(6), ev.synthetic_test_set(6)
     assert all(np.array_equal(p[2], q[2]) for p, q in zip(a, b))
     assert all(16000 <= len(p[2]) <= 160000 for p in a)
+
+
+def test_load_reference_style_checkpoint_with_pickled_data_module_cls(tmp_path, synthetic_sd):
+    """a checkpoint as the reference writes it - Lightning layout, torch_ema state under 'ema', and
+    hyper_parameters['data_module_cls'] pickled BY REFERENCE as flowmse.data_module.SpecsDataModule - loads without the
+    reference package installed; EMA weights become live on eval(), no_ema keeps the raw ones (model.py:92-106)."""
+    import sys
+    from flowmse_b200 import checkpoint as ck
+    from flowmse_b200.model import VFModel, reference_pickle_shims
+    ema = {k: v + 0.25 for k, v in synthetic_sd.items()}
+    hp = dict(ck.DEFAULT_HPARAMS)
+    with reference_pickle_shims():                       # the writer side: the class object the reference would pickle
+        import flowmse.data_module as dm
+        hp["data_module_cls"] = dm.SpecsDataModule
+        c = ck.make_lightning_checkpoint(synthetic_sd, ema, hparams=hp, include_frozen_in_ema=False)
+        path = tmp_path / "epoch=7-pesq=2.50.ckpt"
+        torch.save(c, path)
+    assert "flowmse.data_module" not in sys.modules      # the shim does not outlive the load / save
+    model = VFModel.load_from_checkpoint(str(path), base_dir="", batch_size=8, num_workers=4, kwargs=dict(gpu=False))
+    assert "flowmse.data_module" not in sys.modules
+    name = "all_modules.4.Conv_0.weight"
+    assert torch.equal(model.dnn.state_dict()[name], synthetic_sd[name])           # live weights after load
+    model.eval(no_ema=False)
+    assert torch.equal(model.dnn.state_dict()[name], ema[name])                    # EMA selected by eval()
+    assert torch.equal(model.dnn.state_dict()["all_modules.0.W"], synthetic_sd["all_modules.0.W"])   # frozen W: 646 shadows
+    model.eval(no_ema=True)
+    assert torch.equal(model.dnn.state_dict()[name], synthetic_sd[name])
+    assert model.ode.sigma_max == hp.get("sigma_max", 0.487) and model.t_eps == hp.get("t_eps", 0.03)
