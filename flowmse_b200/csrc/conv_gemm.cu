@@ -89,30 +89,6 @@ struct GemmParams {
   int cluster_s;
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of the same shared-memory location in CTA `rank` of this cluster
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
-  float4 v;
-  // not volatile / no memory clobber: the peers' tiles are immutable between the two cluster barriers, and the S loads
-  // of a row must be in flight together
-  asm("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
-      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr));
-  return v;
-}
-
 struct CtaTile { int b, h0, w0, n0; };
 
 // Split-K cluster reduction of one thread: CTA z of an S-CTA cluster owns rows [z*128/S, (z+1)*128/S) of the tile; warp rg
@@ -145,7 +121,7 @@ __device__ __forceinline__ void cluster_reduce_rows(const GemmParams& p, const C
       } else {
         const uint32_t local = red0 + static_cast<uint32_t>((r * RED_STRIDE + 4 * c4) * 4);
 #pragma unroll
-        for (int zz = 0; zz < S; ++zz) pv[i][zz] = ld_dsmem_f4(map_to_cta(local, static_cast<uint32_t>(zz)));
+        for (int zz = 0; zz < S; ++zz) pv[i][zz] = ptx::ld_dsmem_f4(ptx::map_to_cta(local, static_cast<uint32_t>(zz)));
       }
     }
   }
@@ -429,11 +405,11 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     __shared__ float s_red[kEpiWarps][32][2];
     const int S = p.cluster_s;
     __syncwarp();
-    cluster_sync_all();                                    // every CTA's tile is parked and visible cluster-wide
+    ptx::cluster_sync_all();                                    // every CTA's tile is parked and visible cluster-wide
     if (threadIdx.x == 64) stamp(6);
     if (warp >= 2) {
       const int etid = threadIdx.x - 64;
-      const int z = static_cast<int>(cluster_ctarank());
+      const int z = static_cast<int>(ptx::cluster_ctarank());
       const int ncol4 = min(BN, p.Cout - n0) >> 2;         // float4 columns of this tile
       const int c4 = etid & 31, rg = etid >> 5;            // fixed column quad per thread, 8 row groups
       const uint32_t red0 = smem_base;
@@ -462,7 +438,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
     __syncwarp();
-    if (!p.partial) cluster_sync_all();                    // no CTA's shared memory goes away while a peer still reads it
+    if (!p.partial) ptx::cluster_sync_all();                    // no CTA's shared memory goes away while a peer still reads it
   }
 
   if (threadIdx.x == 64) stamp(4);
@@ -573,27 +549,9 @@ __global__ void conv_gemm_simt_kernel(const __half* __restrict__ A, const __half
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn(std::string* err) {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* sym = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) {
-    if (err) *err = std::string("cuTensorMapEncodeTiled not available: ") + cudaGetErrorString(e);
-    return nullptr;
-  }
-  fn = reinterpret_cast<EncodeTiledFn>(sym);
-  return fn;
-}
-
 // activations [2][B][H][W][C] fp16 -> 5-D map, box {64, TW, TH, 1, 1}
 bool make_act_map(CUtensorMap* m, const __half* base, int B, int H, int W, int C, int TW, int TH, std::string* err) {
-  EncodeTiledFn enc = get_encode_fn(err);
+  EncodeTiledFn enc = tensor_map_encoder(err);
   if (!enc) return false;
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 2};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
@@ -608,28 +566,6 @@ bool make_act_map(CUtensorMap* m, const __half* base, int B, int H, int W, int C
       char buf[256];
       snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(act B=%d H=%d W=%d C=%d TW=%d TH=%d) failed: %d", B, H, W, C,
                TW, TH, (int)r);
-      *err = buf;
-    }
-    return false;
-  }
-  return true;
-}
-
-// weights [2][Npad][K] fp16 -> 3-D map, box {64, BN, 1}
-bool make_w_map(CUtensorMap* m, const __half* base, int Npad, int K, int BN, std::string* err) {
-  EncodeTiledFn enc = get_encode_fn(err);
-  if (!enc) return false;
-  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Npad, 2};
-  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)Npad * K * 2};
-  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    if (err) {
-      char buf[256];
-      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(weights Npad=%d K=%d BN=%d) failed: %d", Npad, K, BN, (int)r);
       *err = buf;
     }
     return false;
@@ -722,7 +658,7 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   if (!make_act_map(&tmA, a.A, a.B, a.H, a.W, a.Cin, p.TW, p.TH, err)) return 1;
   if (a.X) { if (!make_act_map(&tmX, a.X, a.B, a.H, a.W, a.Cin2, p.TW, p.TH, err)) return 1; }
   else tmX = tmA;
-  if (!make_w_map(&tmW, a.Wp, a.Npad, K, BN, err)) return 1;
+  if (!make_weight_map(&tmW, a.Wp, a.Npad, K, BN, err)) return 1;
   dim3 grid(a.B * p.tiles_w * p.tiles_h, (a.Cout + BN - 1) / BN);
   // split-K when the output has too few tiles to fill the GPU (needs ldc == Cout so partial planes are dense)
   const int tiles = grid.x * grid.y;
@@ -824,6 +760,45 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-map helpers shared by the two conv kernels (declared in flowse_internal.h)
+// ------------------------------------------------------------------------------------------------
+EncodeTiledFn tensor_map_encoder(std::string* err) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) {
+    if (err) *err = std::string("cuTensorMapEncodeTiled not available: ") + cudaGetErrorString(e);
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+// weights [2][Npad][K] fp16 -> 3-D map, box {64, rows, 1}
+bool make_weight_map(CUtensorMap* m, const __half* base, int Npad, int K, int rows, std::string* err) {
+  EncodeTiledFn enc = tensor_map_encoder(err);
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Npad, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)Npad * K * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(weights Npad=%d K=%d rows=%d) failed: %d", Npad, K, rows, (int)r);
+      *err = buf;
+    }
+    return false;
+  }
+  return true;
+}
 
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   if (!check_args(a, err)) return 1;

@@ -121,24 +121,6 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of the same shared-memory location in CTA `rank` of this cluster
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
 // TMA loads of a CTA pair: data lands in the executing CTA, the transaction bytes complete on `bar`, which may live in
 // the peer (leader) CTA
 __device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
@@ -206,7 +188,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nchunks = p.nchunk_main + p.nchunk_sc;
-  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int rank = PAIR ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   const int item0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int item_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   constexpr int kCtas = PAIR ? 2 : 1;
@@ -226,7 +208,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if constexpr (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
+  if constexpr (PAIR) ptx::cluster_sync_all();      // the peer's barriers are initialised before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot_ptr;
   pdl_wait();                 // barriers, TMEM and tensor maps were set up while the previous kernel drained
@@ -238,7 +220,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t aph = 0, bph = 0;
       long long w_pa = 0, w_pb = 0;            // cycles the producer waited for a free A / B stage
       // PAIR: the full barriers that count are the leader's; this CTA's loads complete there
-      auto full_addr = [&](uint32_t local) { return PAIR ? map_to_cta(local, 0) : local; };
+      auto full_addr = [&](uint32_t local) { return PAIR ? ptx::map_to_cta(local, 0) : local; };
       auto issue_A = [&](int item, int c) {
         const TileCoord t = decode_tile<BN, PAIR>(p, item, rank);
         { const long long c0 = clock64(); ptx::mbar_wait(a_empty(as), aph ^ 1u); w_pa += clock64() - c0; }
@@ -395,9 +377,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int buf = it % C::NBUF;
       const uint32_t use = static_cast<uint32_t>(it / C::NBUF);
       // the accumulator-empty barrier that counts is the leader's
-      const uint32_t t_empty_bar = (PAIR && rank != 0) ? map_to_cta(t_empty(buf), 0) : t_empty(buf);
+      const uint32_t t_empty_bar = (PAIR && rank != 0) ? ptx::map_to_cta(t_empty(buf), 0) : t_empty(buf);
       auto release_tmem = [&]() {
-        if constexpr (PAIR) { if (rank != 0) mbar_arrive_cluster(t_empty_bar); else ptx::mbar_arrive(t_empty_bar); }
+        if constexpr (PAIR) { if (rank != 0) ptx::mbar_arrive_cluster(t_empty_bar); else ptx::mbar_arrive(t_empty_bar); }
         else ptx::mbar_arrive(t_empty_bar);
       };
       const float* brow = p.bias + static_cast<size_t>(t.b) * p.bias_bstride;
@@ -520,7 +502,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   ptx::tc_fence_before();
   __syncthreads();
-  if constexpr (PAIR) cluster_sync_all();      // neither CTA's shared memory / TMEM goes away while the peer may touch it
+  if constexpr (PAIR) ptx::cluster_sync_all();      // neither CTA's shared memory / TMEM goes away while the peer may touch it
   if (warp == 2) {
     ptx::tc_fence_after();
     if constexpr (PAIR) tmem_dealloc_pair(tmem_acc, C::TMEM_COLS);
@@ -528,27 +510,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn(std::string* err) {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* sym = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) {
-    if (err) *err = std::string("cuTensorMapEncodeTiled not available: ") + cudaGetErrorString(e);
-    return nullptr;
-  }
-  fn = reinterpret_cast<EncodeTiledFn>(sym);
-  return fn;
-}
-
 // activations [2][B][H][W][C] fp16 -> 5-D map, box {64 ch, TW+2, TH+2, 1, 1}
 bool make_halo_map(CUtensorMap* m, const __half* base, int B, int H, int W, int C, std::string* err) {
-  EncodeTiledFn enc = encode_fn(err);
+  EncodeTiledFn enc = tensor_map_encoder(err);
   if (!enc) return false;
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 2};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
@@ -564,23 +528,6 @@ bool make_halo_map(CUtensorMap* m, const __half* base, int B, int H, int W, int 
       snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(halo B=%d H=%d W=%d C=%d) failed: %d", B, H, W, C, (int)r);
       *err = buf;
     }
-    return false;
-  }
-  return true;
-}
-
-bool make_w_map(CUtensorMap* m, const __half* base, int Npad, int K, int BN, std::string* err) {
-  EncodeTiledFn enc = encode_fn(err);
-  if (!enc) return false;
-  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Npad, 2};
-  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)Npad * K * 2};
-  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    if (err) *err = "cuTensorMapEncodeTiled(halo weights) failed: " + std::to_string((int)r);
     return false;
   }
   return true;
@@ -623,7 +570,7 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   if (!make_halo_map(&tmA, a.A, a.B, a.H, a.W, a.Cin, err)) return 1;
   if (a.X) { if (!make_halo_map(&tmX, a.X, a.B, a.H, a.W, a.Cin2, err)) return 1; }
   else tmX = tmA;
-  if (!make_w_map(&tmW, a.Wp, a.Npad, K, C::B_ROWS, err)) return 1;
+  if (!make_weight_map(&tmW, a.Wp, a.Npad, K, C::B_ROWS, err)) return 1;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[2];
   cfg.blockDim = dim3(NUM_THREADS);

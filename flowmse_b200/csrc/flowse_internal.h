@@ -1,5 +1,6 @@
 // Internal declarations shared by the .cu translation units of libflowse.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cstddef>
@@ -168,6 +169,13 @@ int launch_conv_gemm_simt(const ConvGemmArgs& a, cudaStream_t s, std::string* er
 // nmain = number of rotating hi*hi accumulator slots (1: double-buffered TMEM, 3: single buffer).
 bool conv_halo_supported(const ConvGemmArgs& a);
 int launch_conv_halo(const ConvGemmArgs& a, int nmain, cudaStream_t s, std::string* err);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda), and the weight
+// tensor map both conv kernels use: [2][Npad][K] fp16 -> 3-D map with box {64, rows, 1}, 128-byte swizzle.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder(std::string* err);
+bool make_weight_map(CUtensorMap* m, const __half* base, int Npad, int K, int rows, std::string* err);
 // Host-side packing: fp32 [Cout][Cin][kh][kw] (+ optional 1x1 shortcut [Cout][Cin2]) -> K-major fp16 hi/lo.
 // out_hi/out_lo: [Npad][K]; returns the power-of-two exponent used.
 int pack_conv_weights_host(const float* w_main, int Cout, int Cin, int ntaps, const float* w_sc, int Cin2,
