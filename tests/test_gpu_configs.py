@@ -112,3 +112,19 @@ def test_config2_N5_euler_chained_steps_property(ctx):
         x = ctx.euler_step(x, v, float(step))
     frac, mx = _frac_bad(x_fused, x)
     assert frac == 0.0, (frac, mx)
+
+
+def test_longest_bucket_T1280_batch_consistency(ctx):
+    """The longest utterances of the VoiceBank-DEMAND-shaped set (10 s -> T = 1280 frames, 256 x 1280 pixels at the top
+    level, 4 x 20 at the bottom: partial 128-pixel tiles on every low-resolution level) and the shortest (T = 64): one NFE
+    (N = 1 Euler) of a batch of two vs each utterance alone - another plan, other tile / split-K cluster choices - must
+    agree within the north-star tolerance on 100 % of the bins, and everything must be finite."""
+    for T in (1280, 64):
+        Y, z = _rand_c((2, 1, 256, T), 51, 0.3).cuda(), _rand_c((2, 1, 256, T), 52, np.sqrt(0.5)).cuda()
+        ts = torch.linspace(1.0, 0.03, 1)
+        xb = ctx.sample(Y, z, ts, solver=0, sigma=0.487)
+        assert torch.isfinite(torch.view_as_real(xb)).all()
+        for i in (0, 1):
+            xi = ctx.sample(Y[i:i + 1].contiguous(), z[i:i + 1].contiguous(), ts, solver=0, sigma=0.487)
+            frac, mx = _frac_bad(xb[i:i + 1], xi)
+            assert frac == 0.0 and mx < 2e-4, (T, i, frac, mx)
