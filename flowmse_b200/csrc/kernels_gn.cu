@@ -15,21 +15,32 @@ namespace flowse {
 
 namespace {
 
-// SiLU with the fast exp / divide intrinsics: |rel err| ~ 2e-7 near 0, absolute error < 1e-9 in the tails.
-__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// SiLU from the two MUFU approximations directly: v * rcp(1 + ex2(-v * log2 e)), 5 instructions.  (__expf / __fdividef
+// wrap the same MUFU.EX2 / MUFU.RCP in denormal-range scaling - FSETP + 2 FMUL per call - which only matters when
+// exp(-v) is denormal, i.e. when 1 + exp(-v) == 1 anyway.)  |rel err| ~ 2e-7 near 0, absolute error < 1e-9 in the tails.
+// Together with the saturating pack below this removes ~6 of the ~25 instructions per element; end to end it measured
+// within noise (22.78-22.86 vs 22.6-22.9 ms per sampler call), kept because it is the simpler code.
+__device__ __forceinline__ float silu_f(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return v * r;
+}
 
-__device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+// two fp32 -> packed fp16x2 (e0 in the low half), round-to-nearest-even, saturating to +-65504 (F2FP.SATFINITE: one
+// instruction, replaces a 2-instruction clamp per element)
+__device__ __forceinline__ uint32_t pack_h2_sat(float e0, float e1) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+  return r;
+}
 
-// exact hi/lo split: v ~= hi + lo with hi, lo fp16 (v saturated to the fp16 range first)
+// exact hi/lo split: v ~= hi + lo with hi, lo fp16 (saturating; lo = v - hi is exact in fp32)
 __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
-  const float a = clamp_h(v.x), b = clamp_h(v.y), c = clamp_h(v.z), d = clamp_h(v.w);
-  const __half ha = __float2half_rn(a), hb = __float2half_rn(b), hc = __float2half_rn(c), hd = __float2half_rn(d);
-  const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
-  const __half lc = __float2half_rn(c - __half2float(hc)), ld = __float2half_rn(d - __half2float(hd));
-  __half2 h01 = __halves2half2(ha, hb), h23 = __halves2half2(hc, hd);
-  __half2 l01 = __halves2half2(la, lb), l23 = __halves2half2(lc, ld);
-  hi.x = *reinterpret_cast<uint32_t*>(&h01); hi.y = *reinterpret_cast<uint32_t*>(&h23);
-  lo.x = *reinterpret_cast<uint32_t*>(&l01); lo.y = *reinterpret_cast<uint32_t*>(&l23);
+  hi.x = pack_h2_sat(v.x, v.y); hi.y = pack_h2_sat(v.z, v.w);
+  const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x));
+  const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+  lo.x = pack_h2_sat(v.x - f01.x, v.y - f01.y); lo.y = pack_h2_sat(v.z - f23.x, v.w - f23.y);
 }
 __device__ __forceinline__ uint4 pack8(const uint2 a, const uint2 b) { return make_uint4(a.x, a.y, b.x, b.y); }
 
