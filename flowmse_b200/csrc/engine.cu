@@ -169,6 +169,9 @@ struct flowse_ctx {
   float* op_scratch = nullptr; size_t op_scratch_bytes = 0;
   float* op_splitk = nullptr;
   // STFT / iSTFT (stft.cu): bases built on first use, scratch grown on demand
+  // one grow-only workspace shared by successive plans (cudaMalloc / cudaFree of multi-GiB arenas on every (B,T) switch
+  // cost up to hundreds of milliseconds in the bucketed evaluate driver)
+  char* arena = nullptr; size_t arena_cap = 0;
   float* stft_basis = nullptr;
   char* stft_scratch = nullptr; size_t stft_scratch_bytes = 0;
 };
@@ -577,8 +580,7 @@ int ensure_plan(flowse_ctx* ctx, int B, int T) {
   if (ctx->plan) {
     CK(cudaDeviceSynchronize());
     if (ctx->plan->graph_fwd) cudaGraphExecDestroy(ctx->plan->graph_fwd);
-    if (ctx->plan->arena) cudaFree(ctx->plan->arena);
-    ctx->plan.reset();
+    ctx->plan.reset();          // the workspace belongs to the context and is reused
   }
   std::unique_ptr<Plan> plan(new Plan());
   plan->B = B; plan->T = T;
@@ -588,8 +590,14 @@ int ensure_plan(flowse_ctx* ctx, int B, int T) {
     plan->arena_bytes = dry.ar.off + 4096;
     plan->taps.clear();
   }
-  CK(cudaMalloc(reinterpret_cast<void**>(&plan->arena), plan->arena_bytes));
-  CK(cudaMemset(plan->arena, 0, plan->arena_bytes));
+  if (ctx->arena_cap < plan->arena_bytes) {
+    if (ctx->arena) { CK(cudaFree(ctx->arena)); ctx->arena = nullptr; ctx->arena_cap = 0; }
+    const size_t cap = plan->arena_bytes + plan->arena_bytes / 8;      // headroom: slightly larger buckets reuse it
+    CK(cudaMalloc(reinterpret_cast<void**>(&ctx->arena), cap));
+    ctx->arena_cap = cap;
+  }
+  plan->arena = ctx->arena;
+  CK(cudaMemset(plan->arena, 0, plan->arena_bytes));       // statistics slots and counters start from zero
   {
     Builder real{ctx, plan.get(), Arena{plan->arena, 0}, false, B, T};
     if (int rc = real.build()) return rc;
@@ -691,8 +699,8 @@ void flowse_destroy(flowse_ctx* ctx) {
   cudaDeviceSynchronize();
   if (ctx->plan) {
     if (ctx->plan->graph_fwd) cudaGraphExecDestroy(ctx->plan->graph_fwd);
-    if (ctx->plan->arena) cudaFree(ctx->plan->arena);
   }
+  if (ctx->arena) cudaFree(ctx->arena);
   for (void* p : ctx->dev_allocs) cudaFree(p);
   if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
   if (ctx->op_stats) cudaFree(ctx->op_stats);
