@@ -41,6 +41,11 @@ T_REV, T_EPS, SIGMA_MAX = 1.0, 0.03, 0.487
 GFLOP_PER_FRAME_NFE = 2.0795
 
 
+def workload_string(B: int = 1) -> str:
+    """config.workload, identical in both arms (the driver compares the strings)."""
+    return f"batch={B} complex-STFT 2x{F_BINS}x{T_FRAMES}, N={N_STEPS_ODE} Euler (BASELINE.json configs[1])"
+
+
 def synth_input(seed: int, B: int = 1, T: int = T_FRAMES) -> torch.Tensor:
     """config 2 input: Y = 0.3 * randn([B,1,256,T]) complex64, seeded."""
     g = torch.Generator().manual_seed(seed)
@@ -126,12 +131,12 @@ def run_reference_arm(args):
     torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     sd = synthetic_state_dict(0)
     cores = torch.get_num_threads()
-    # each step = the bench workload itself when the host is fast enough for (K + W) steps to end within ~150 s, else a
-    # bounded slice of it (the cost is linear in T): calibrated on one T=64 evaluation
+    # each step = the bench workload ITSELF (one N=5 Euler sampler call on [1,1,256,512]).  Only when the host is so slow
+    # that K + W steps would take more than 15 minutes is a slice of it used, and then config.reference_T says so.
     t_cal = cpu_sampler_seconds(sd, 64, 1)
     t_cal = min(t_cal, cpu_sampler_seconds(sd, 64, 1))
     T_s = T_FRAMES
-    while T_s > 64 and (args.steps + args.warmup) * t_cal * N_STEPS_ODE * (T_s / 64.0) > 150.0:
+    while T_s > 64 and (args.steps + args.warmup) * t_cal * N_STEPS_ODE * (T_s / 64.0) > 900.0:
         T_s //= 2
     for _ in range(args.warmup):
         cpu_sampler_seconds(sd, T_s, N_STEPS_ODE)
@@ -147,7 +152,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batch=1 complex-STFT 2x256x{T_FRAMES}, N=5 Euler (configs[1])"},
+        "config": {"workload": workload_string(1), "reference_T": T_s,
+                   "reference_T_note": "frames per step the CPU arm actually ran (== the workload's 512 unless stated)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -156,6 +162,83 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------------------
+def torch_cuda_reference(dev, value, e2e_val):
+    """N=5 Euler on [1,1,256,512] through torch-CUDA (oracle restatement on cuda:0), TF32 off and on."""
+    from oracle import ncsnpp_oracle as orc
+    from flowmse_b200.checkpoint import synthetic_state_dict
+    sd_cuda = {k: v.to(dev) for k, v in synthetic_state_dict(0).items()}
+    Y = synth_input(1000, 1).to(dev)
+    z = torch.view_as_complex(torch.randn(1, 1, F_BINS, T_FRAMES, 2, generator=torch.Generator().manual_seed(1234)) * (0.5 ** 0.5)).to(dev)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    out = {"measured_in_this_run": True, "workload": workload_string(1),
+           "what": "oracle restatement of the reference path evaluated by torch on cuda:0 (cuDNN / ATen), eager, CUDA events, "
+                   "1 warm-up + 3 timed sampler calls per setting"}
+    xs = {}
+    try:
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.device(dev):
+                orc.sample(sd_cuda, Y, z, N_STEPS_ODE)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    xs[name] = orc.sample(sd_cuda, Y, z, N_STEPS_ODE)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            out[f"{name}_ms_per_step"] = ms
+            out[f"{name}_frames_per_s"] = T_FRAMES / (ms * 1e-3)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    a, b = torch.view_as_real(xs["tf32"]), torch.view_as_real(xs["fp32"])
+    out["tf32_frac_outside_tolerance_vs_fp32"] = ((a - b).abs() > 1e-4 + 1e-3 * b.abs()).float().mean().item()
+    out["ours_over_fp32"] = value / out["fp32_frames_per_s"]
+    out["ours_over_tf32"] = value / out["tf32_frames_per_s"]
+    out["ours_e2e_over_tf32"] = e2e_val / out["tf32_frames_per_s"]
+    return out
+
+
+def run_config4(args, model, ctx, dev, world, rank, dist):
+    """BASELINE.json configs[3]: 512 synthetic utterances x [1,1,256,512], N=5 Euler, sharded over the ranks by
+    flowmse_b200.sharding.enhance_sharded (length-aware LPT assignment, batches of 16, ragged all-gather of the enhanced
+    spectrograms over NCCL) - STRONG scaling: the total work is fixed, the window holds sampling + gather."""
+    from flowmse_b200 import sharding
+    n_utts = args.config4 if args.config4 > 0 else 512
+    # every rank holds the same utterance list (a fixed block of 16 distinct spectrograms, reused: HBM-resident inputs)
+    base = synth_input(4242, 16).to(dev)
+    specs = [base[i % 16] for i in range(n_utts)]
+
+    def enhance(Yb):
+        return model.enhance_spec(Yb, N=N_STEPS_ODE)
+
+    def once():
+        return sharding.enhance_sharded(specs, enhance, dev, max_batch=16)
+
+    torch.manual_seed(99 + rank)
+    warm = [specs[i] for i in range(min(n_utts, 16 * world))]
+    sharding.enhance_sharded(warm, enhance, dev, max_batch=16)        # plan + graphs for the (16, 512) shape, warm gather
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = once()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    assert len(out) == n_utts and all(o.shape[-1] == T_FRAMES for o in out)
+    return {"workload": f"{n_utts} utterances x [1,1,256,{T_FRAMES}], N=5 Euler, batches of 16, sharded over {world} GPU(s) "
+                        f"+ ragged all-gather (BASELINE.json configs[3])",
+            "scaling": "strong", "n_gpus": world, "ms": ms.item(), "value": n_utts * T_FRAMES / (ms.item() * 1e-3),
+            "unit": UNIT, "gathered_bytes": n_utts * F_BINS * T_FRAMES * 8}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from flowmse_b200.checkpoint import synthetic_state_dict, flatten_state_dict, unflatten_state_dict
@@ -211,34 +294,44 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather_result(last):
+        """the job's single gather of enhanced spectrograms (1 MiB per rank here)"""
+        if world > 1:
+            gathered = [torch.empty_like(torch.view_as_real(last)) for _ in range(world)]
+            dist.all_gather(gathered, torch.view_as_real(last).contiguous())
+
     def timed(fn, steps, warmup):
+        last = None
         for _ in range(warmup):
-            fn()
+            last = fn()
+        gather_result(last)              # the collective is warmed like everything else in the window
         barrier()
         l0 = ctx.kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.time()
         e0.record()
-        last = None
         for _ in range(steps):
             last = fn()
-        if world > 1:   # the job's single gather of enhanced spectrograms
-            gathered = [torch.empty_like(torch.view_as_real(last)) for _ in range(world)]
-            dist.all_gather(gathered, torch.view_as_real(last).contiguous())
+        gather_result(last)
         e1.record()
         barrier()
         w1 = time.time()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        mine = e0.elapsed_time(e1)
+        ms = torch.tensor([mine], device=dev)
+        per_rank = [mine]
         if world > 1:
+            allms = [torch.empty_like(ms) for _ in range(world)]
+            dist.all_gather(allms, ms)
+            per_rank = [float(v.item()) for v in allms]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), ctx.kernel_launches() - l0, (w0, w1)
+        return ms.item(), ctx.kernel_launches() - l0, (w0, w1), per_rank
 
     clocks = ClockSampler(local_rank)
     clocks.start()
     time.sleep(0.3)
-    ms_dev, launches, (w0, w1) = timed(step_device, args.steps, args.warmup)
+    ms_dev, launches, (w0, w1), per_rank_ms = timed(step_device, args.steps, args.warmup)
     clk = clocks.stop(w0, w1)
-    ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps, args.warmup)
 
     frames_per_step = B * T_FRAMES * world
     value = frames_per_step * args.steps / (ms_dev * 1e-3)
@@ -249,8 +342,9 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batch={B} complex-STFT 2x{F_BINS}x{T_FRAMES} per GPU, N=5 Euler, sigma_max=0.487 "
-                               f"(BASELINE.json configs[1]); synthetic seeded weights (65.6 M params)",
+        "config": {"workload": workload_string(B),
+                   "per_gpu": "one such batch per GPU per step (weak scaling), sigma_max=0.487, synthetic seeded weights "
+                              "(65.6 M params); one NCCL weight broadcast before, one all-gather of the outputs inside the window",
                    "l2": "working set > L2: 250 MiB packed weights + ~1.3 GiB activations per NFE vs 126 MB L2",
                    "arithmetic": "fp32 parity via fp16 hi/lo split on tcgen05 (3 MMAs per product), fp32 accumulate"},
         "clocks": clk,
@@ -258,6 +352,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": out_host.numel() * 8, "ms_per_step": ms_e2e / args.steps,
                 "api": "flowmse_b200.sampling.get_white_box_solver(...)() with pinned host Y, result copied to host"},
         "gpu_launches": int(launches),
+        "per_rank_ms_per_step": [round(v / args.steps, 4) for v in per_rank_ms],
     }
 
     if rank == 0:
@@ -370,14 +465,27 @@ def run_ours(args):
                 "sample": f"oracle port (torch CPU fp32 restatement of the reference path), {reps} full N=5 Euler sampler calls "
                           f"on the bench workload [1,1,256,{T_FRAMES}] ({secs:.1f} s), {cores} threads of {os.cpu_count()} "
                           f"host cores"}
-        try:    # informational: the torch-CUDA evaluation of the same path measured by tests/test_gpu_torch_cuda.py
-            tc = json.load(open(os.path.join(ROOT, "profiles", "r1b_torch_cuda_baseline.json")))
-            result["gpu_torch_reference"] = {
-                "fp32_frames_per_s": tc["torch_cuda_fp32_frames_per_s"], "tf32_frames_per_s": tc["torch_cuda_tf32_frames_per_s"],
-                "tf32_frac_outside_tolerance": tc["tf32_vs_fp32"]["frac_outside_tol"],
-                "note": "committed measurement (profiles/r1b_torch_cuda_baseline.json), not re-measured in this run"}
-        except Exception:
-            pass
+        # ---- the same path evaluated by PyTorch on this GPU, measured in this run (BASELINE.json configs[1]: "vs reference
+        # torch-cuda").  The reference package cannot travel to the GPU box, so this is its restatement (oracle/) run with
+        # every tensor on cuda:0 - the ATen ops the reference dispatches: cuDNN convolutions, native_group_norm, bmm,
+        # softmax - timed with CUDA events after a warm-up call, TF32 off (fp32: the parity setting) and on (PyTorch's
+        # default for convolutions: the speed baseline).  It is a checker timed beside the product, never part of it.
+        if not args.no_torch_reference and world == 1:
+            try:
+                result["gpu_torch_reference"] = torch_cuda_reference(dev, value, e2e_val)
+            except Exception as e:
+                result["gpu_torch_reference"] = {"error": f"{type(e).__name__}: {e}"}
+    # ---- BASELINE.json configs[3], strong scaling (every rank takes part; reported beside the weak-scaling headline).
+    # Runs last: it re-plans the context for batches of 16.
+    if args.config4 != 0:
+        try:
+            c4 = run_config4(args, model, ctx, dev, world, rank, dist)
+        except Exception as e:
+            if world > 1:
+                raise
+            c4 = {"error": f"{type(e).__name__}: {e}"}
+        result["extra"] = {"config4_strong_scaling": c4}
+    if rank == 0:
         print(json.dumps(result))
     if world > 1:
         dist.barrier()
@@ -392,6 +500,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-reference", action="store_true", help="skip the live torch-CUDA measurement (N=1 only)")
+    ap.add_argument("--config4", type=int, default=-1,
+                    help="utterances of the configs[3] strong-scaling leg reported in extra (-1 = 512, 0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -64,6 +64,7 @@ class NCSNpp(nn.Module):
         self.output_layer = _ParamHolder([("weight", (2, spec.NUM_CHANNELS, 1, 1)), ("bias", (2,))])
         self.all_modules = nn.ModuleList([_ParamHolder(spec.module_params(m)) for m in spec.module_list()])
         self._ctx = {}           # device index -> (Context, version stamp)
+        self._stamp, self._sentinels = 0, None
         self._reset_like_reference(fourier_scale)
 
     def _reset_like_reference(self, fourier_scale):
@@ -89,7 +90,28 @@ class NCSNpp(nn.Module):
 
     # ---- libflowse context management --------------------------------------------------------------------------
     def _version(self):
-        return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+        """Stamp of the live weights.  Every bulk update path (load_state_dict, an EMA swap, optimiser steps) rewrites ALL
+        parameters in place, which bumps each tensor's autograd version counter; a few sentinels therefore identify the
+        state without walking all 647 tensors on every sampler call.  ``invalidate()`` forces a re-pack after any other
+        kind of edit."""
+        s = self._sentinels
+        if s is None:
+            ps = list(self.parameters())
+            s = self._sentinels = [ps[0], ps[len(ps) // 3], ps[(2 * len(ps)) // 3], ps[-1]]
+        return (self._stamp,) + tuple(p._version for p in s) + tuple(p.data_ptr() for p in s)
+
+    def invalidate(self):
+        """Declare the parameters changed: the next call re-packs them into the libflowse context."""
+        self._stamp += 1
+        self._sentinels = None
+
+    def _load_from_state_dict(self, *a, **k):
+        self.invalidate()
+        return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):          # .to() / .cuda() / .half() replace the parameter tensors
+        self.invalidate()
+        return super()._apply(fn, *a, **k)
 
     def flowse_context(self, device):
         """The libflowse context holding THIS module's weights on `device` (packed on first use, re-packed when a

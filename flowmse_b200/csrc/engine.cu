@@ -122,6 +122,9 @@ struct Act { float* p = nullptr; int C = 0, H = 0, W = 0; double* qs = nullptr; 
 //       6 time embedding, 7 conv_halo (halo kernel; chosen at plan time with the conv_impl option in force)
 struct Op { std::function<int(cudaStream_t)> fn; int nk; int kind; double flops; int info[4]; };
 
+struct Plan;
+void destroy_graphs(Plan* p);
+
 struct Plan {
   int B = 0, T = 0;
   char* arena = nullptr;
@@ -139,7 +142,20 @@ struct Plan {
   cudaGraphExec_t graph_fwd = nullptr;      // forward, final mode 0/1 chosen at launch via separate final op
   bool graph_ready = false;
   int eager_runs = 0;   // the first evaluation of a plan runs eagerly (sets kernel attributes, surfaces errors)
+  // time embedding: a function of t only, so it is NOT part of the replayed evaluation.  flowse_sample evaluates it for
+  // every time point of the schedule in one launch pair (rows = evaluations x B) and copies row block e into the
+  // fixed bias table before evaluation e; flowse_ncsnpp_forward runs it for its B rows.
+  std::function<int(const float* t_rows, int rows, float* table, cudaStream_t)> temb_fn;
+  float* bias_table = nullptr;              // [B][R], read by the Conv_0 epilogues
+  float* t_all = nullptr;                   // [kMaxEvals * B] evaluation times of a sampler call
+  float* temb_all = nullptr;                // [kMaxEvals * B][512]
+  float* bias_all = nullptr;                // [kMaxEvals][B][R]
+  float2* yp = nullptr;                     // prior mean when it differs from y
+  // whole-sampler graphs (prior + every evaluation + fused updates), keyed by schedule / solver / sigma
+  struct SamplerGraph { std::vector<float> ts; int solver; float sigma; bool own_prior; cudaGraphExec_t exec; long long kernels; int seen; };
+  std::vector<SamplerGraph> sampler_graphs;
 };
+constexpr int kMaxEvals = 64;               // evaluations whose time embeddings are computed by one launch pair
 
 }  // namespace
 
@@ -174,6 +190,10 @@ struct flowse_ctx {
   char* arena = nullptr; size_t arena_cap = 0;
   float* stft_basis = nullptr;
   char* stft_scratch = nullptr; size_t stft_scratch_bytes = 0;
+  // sticky fp16 range flag: operand-producing kernels count the values whose magnitude exceeds the fp16 hi/lo range
+  // (|v| > 65504 saturates silently otherwise); read back through flowse_fp16_overflow
+  unsigned long long* overflow = nullptr;
+  int whole_graph = 1;                      // capture the whole sampler call as one CUDA graph (second call with the same schedule)
 };
 
 namespace {
@@ -401,7 +421,7 @@ struct Builder {
     pa.src1 = s1; pa.C1 = C1; pa.src2 = s2; pa.C2 = C2; pa.qs1 = in1.qs; pa.qs2 = in2 ? in2->qs : nullptr;
     pa.gamma = r.gn0_g; pa.beta = r.gn0_b;
     pa.B = B; pa.H = H; pa.W = W; pa.mode = r.down ? kPrepDown : (r.up ? kPrepUp : kPrepPlain); pa.silu = 1;
-    pa.outA = scrA; pa.outX = r.has_sc ? scrX : nullptr;
+    pa.outA = scrA; pa.outX = r.has_sc ? scrX : nullptr; pa.overflow = ctx->overflow;
     push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; }, 2);
     ConvGemmArgs c0{};
     c0.A = scrA; c0.Cin = Cin; c0.ntaps = 9; c0.X = nullptr; c0.Cin2 = 0; c0.Wp = r.conv0.wp; c0.Npad = r.conv0.Npad;
@@ -413,7 +433,7 @@ struct Builder {
     float* h1 = scrH1; const int Co = r.cout;
     PrepArgs pb{};
     pb.src1 = h1; pb.C1 = Co; pb.src2 = nullptr; pb.C2 = 0; pb.qs1 = st1; pb.gamma = r.gn1_g; pb.beta = r.gn1_b;
-    pb.B = B; pb.H = Ho; pb.W = Wo; pb.mode = kPrepPlain; pb.silu = 1; pb.outA = scrA;
+    pb.B = B; pb.H = Ho; pb.W = Wo; pb.mode = kPrepPlain; pb.silu = 1; pb.outA = scrA; pb.overflow = ctx->overflow;
     push(1, [=](cudaStream_t s) { launch_gn_prep(pb, s); return 0; }, 2);
     ConvGemmArgs c1{};
     c1.A = scrA; c1.Cin = Co; c1.ntaps = 9; c1.X = r.has_sc ? scrX : nullptr; c1.Cin2 = r.has_sc ? Cin : 0;
@@ -477,9 +497,14 @@ struct Builder {
     plan->x = ar.alloc<float2>(B * HW); plan->y = ar.alloc<float2>(B * HW); plan->z = ar.alloc<float2>(B * HW);
     plan->vout = ar.alloc<float2>(B * HW); plan->xa = ar.alloc<float2>(B * HW);
     plan->va = ar.alloc<float2>(B * HW); plan->vb = ar.alloc<float2>(B * HW);
+    plan->yp = ar.alloc<float2>(B * HW);
     plan->t_dev = ar.alloc<float>(B); plan->step_dev = ar.alloc<float>(4);
     temb_act = ar.alloc<float>(static_cast<size_t>(B) * kTemb);
     bias_table = ar.alloc<float>(static_cast<size_t>(B) * ctx->dense_rows);
+    plan->bias_table = bias_table;
+    plan->t_all = ar.alloc<float>(static_cast<size_t>(kMaxEvals) * B);
+    plan->temb_all = ar.alloc<float>(static_cast<size_t>(kMaxEvals) * B * kTemb);
+    plan->bias_all = ar.alloc<float>(static_cast<size_t>(kMaxEvals) * B * ctx->dense_rows);
     // scratch sized for the largest user (level 0, 256 concatenated input channels)
     const size_t top = static_cast<size_t>(B) * HW;
     scrA = ar.alloc<__half>(2 * top * 256);
@@ -498,8 +523,10 @@ struct Builder {
 
     // ---- the walk (ncsnpp.py:247-404) ----
     {
-      TembWeights tw = ctx->temb; float* td = plan->t_dev; float* ta = temb_act; float* bt = bias_table; const int Bc = B;
-      push(2, [=](cudaStream_t s) { launch_temb(tw, td, Bc, ta, bt, s); return 0; }, 6);
+      // the time embedding is a prologue outside the replayed op list (see Plan::temb_fn)
+      TembWeights tw = ctx->temb; float* ta = plan->temb_all;
+      if (!dry) plan->temb_fn = [=](const float* t_rows, int rows, float* table, cudaStream_t s) {
+        launch_temb(tw, t_rows, rows, ta, table, s); return 0; };
       // producers accumulate quad statistics with atomics: clear all slots once per evaluation
       double* st = plan->stats; const size_t sb = plan->stats_bytes;
       push(0, [=](cudaStream_t s) { return cudaMemsetAsync(st, 0, sb, s) == cudaSuccess ? 0 : 1; }, 0);
@@ -572,14 +599,23 @@ struct Builder {
   }
 };
 
-int ensure_plan(flowse_ctx* ctx, int B, int T) {
+void destroy_graphs(Plan* p) {
+  if (p->graph_fwd) { cudaGraphExecDestroy(p->graph_fwd); p->graph_fwd = nullptr; }
+  p->graph_ready = false;
+  for (auto& g : p->sampler_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  p->sampler_graphs.clear();
+}
+
+// `s` is the stream the caller is about to enqueue work on: the plan's zero-initialisation is ordered on it (a
+// synchronous cudaMemset runs on the legacy NULL stream, which non-blocking streams are not ordered against).
+int ensure_plan(flowse_ctx* ctx, int B, int T, cudaStream_t s) {
   if (!ctx->weights_loaded) { ctx->err = "weights not loaded (call flowse_load_weights first)"; return 2; }
   if (B <= 0 || T <= 0 || T % 64 != 0) { ctx->err = "need B > 0 and T a positive multiple of 64 (pad_spec)"; return 2; }
   if (ctx->plan && ctx->plan->B == B && ctx->plan->T == T) return 0;
   CK(cudaSetDevice(ctx->device));
   if (ctx->plan) {
     CK(cudaDeviceSynchronize());
-    if (ctx->plan->graph_fwd) cudaGraphExecDestroy(ctx->plan->graph_fwd);
+    destroy_graphs(ctx->plan.get());
     ctx->plan.reset();          // the workspace belongs to the context and is reused
   }
   std::unique_ptr<Plan> plan(new Plan());
@@ -597,11 +633,16 @@ int ensure_plan(flowse_ctx* ctx, int B, int T) {
     ctx->arena_cap = cap;
   }
   plan->arena = ctx->arena;
-  CK(cudaMemset(plan->arena, 0, plan->arena_bytes));       // statistics slots and counters start from zero
   {
     Builder real{ctx, plan.get(), Arena{plan->arena, 0}, false, B, T};
     if (int rc = real.build()) return rc;
   }
+  // only the statistics slots and the last-block counters need to start from zero (every evaluation clears the slots
+  // again; the counters are restored to zero by their kernel).  Ordered on the caller's stream, then waited for, so a
+  // later call on another stream cannot overtake it.
+  CK(cudaMemsetAsync(plan->stats, 0, plan->stats_bytes, s));
+  CK(cudaMemsetAsync(plan->gn_counters, 0, sizeof(unsigned) * B, s));
+  CK(cudaStreamSynchronize(s));
   plan->kernels_per_forward = 0;
   for (const auto& op : plan->ops) plan->kernels_per_forward += op.nk;
   ctx->plan = std::move(plan);
@@ -617,9 +658,11 @@ int run_ops(flowse_ctx* ctx, cudaStream_t s) {
   return 0;
 }
 
-// One network evaluation on the plan's fixed buffers (x, y, t_dev) -> pyr_out.
-int run_backbone(flowse_ctx* ctx, cudaStream_t s) {
+// One network evaluation on the plan's fixed buffers (x, y, t_dev, bias_table) -> pyr_out.  inline_ops: enqueue the ops
+// themselves even when a per-evaluation graph exists (used while a whole sampler call is being captured).
+int run_backbone(flowse_ctx* ctx, cudaStream_t s, bool inline_ops = false) {
   Plan* p = ctx->plan.get();
+  if (inline_ops) return run_ops(ctx, s);
   if (ctx->use_graph && p->eager_runs >= 1) {
     if (!p->graph_ready) {
       cudaGraph_t g = nullptr;
@@ -689,6 +732,12 @@ int flowse_create(flowse_ctx** out, int device) {
   ctx->mods = build_modules();
   ctx->counter_base = launch_counter();
   cudaSetDevice(device);
+  if (cudaMalloc(reinterpret_cast<void**>(&ctx->overflow), sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(ctx->overflow, 0, sizeof(unsigned long long)) != cudaSuccess) {
+    g_create_error = "cudaMalloc failed in flowse_create";
+    delete ctx;
+    return 1;
+  }
   *out = ctx;
   return 0;
 }
@@ -697,9 +746,8 @@ void flowse_destroy(flowse_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  if (ctx->plan) {
-    if (ctx->plan->graph_fwd) cudaGraphExecDestroy(ctx->plan->graph_fwd);
-  }
+  if (ctx->plan) destroy_graphs(ctx->plan.get());
+  if (ctx->overflow) cudaFree(ctx->overflow);
   if (ctx->arena) cudaFree(ctx->arena);
   for (void* p : ctx->dev_allocs) cudaFree(p);
   if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
@@ -735,7 +783,7 @@ int flowse_load_weights(flowse_ctx* ctx, const float* host_blob, const flowse_te
 size_t flowse_workspace_bytes(flowse_ctx* ctx, int B, int T) {
   if (!ctx) return 0;
   ctx->err.clear();
-  if (ensure_plan(ctx, B, T)) return 0;
+  if (ensure_plan(ctx, B, T, nullptr)) return 0;
   return ctx->plan->arena_bytes;
 }
 
@@ -764,18 +812,106 @@ int flowse_ncsnpp_forward(flowse_ctx* ctx, const void* x, long long x_bstride, c
                           const float* t, void* out, int negate, int B, int T, void* stream) {
   if (!ctx) return 2;
   ctx->err.clear();
-  if (int rc = ensure_plan(ctx, B, T)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = ensure_plan(ctx, B, T, s)) return rc;
   Plan* p = ctx->plan.get();
   const size_t row = static_cast<size_t>(kImage) * T * sizeof(float2);
   CK(cudaMemcpy2DAsync(p->x, row, x, x_bstride * sizeof(float2), row, B, cudaMemcpyDeviceToDevice, s));
   CK(cudaMemcpy2DAsync(p->y, row, y, y_bstride * sizeof(float2), row, B, cudaMemcpyDeviceToDevice, s));
   CK(cudaMemcpyAsync(p->t_dev, t, sizeof(float) * B, cudaMemcpyDeviceToDevice, s));
+  if (int rc = p->temb_fn(p->t_dev, B, p->bias_table, s)) return rc;
   if (int rc = run_backbone(ctx, s)) return rc;
   final_op(ctx, negate ? 1 : 0, nullptr, static_cast<float2*>(out), s);
   CK(cudaGetLastError());
   return 0;
 }
+
+}  // extern "C"
+
+namespace {
+
+// Times at which a sampler call evaluates the network, in order (sampling/__init__.py:48-57 for Euler; SURVEY.md 8 A4 for
+// Heun / midpoint with an Euler step on the last interval).  fp32 arithmetic, as the reference's tensors.
+std::vector<float> evaluation_times(const float* ts, int N, int solver) {
+  std::vector<float> ev;
+  for (int i = 0; i < N; ++i) {
+    const float t = ts[i];
+    const float step = (i != N - 1) ? (t - ts[i + 1]) : ts[N - 1];
+    ev.push_back(t);
+    if (solver != FLOWSE_SOLVER_EULER && i != N - 1) {
+      const float dt = -step;
+      ev.push_back(solver == FLOWSE_SOLVER_HEUN ? t + dt : t + dt / 2);
+    }
+  }
+  return ev;
+}
+
+// Everything of a sampler call between "y, z (and yp) are in the plan's buffers" and "the result is in p->x", enqueued
+// on s.  inline_ops: see run_backbone.
+int enqueue_sampler(flowse_ctx* ctx, const float* ts, int N, int solver, float sigma, bool own_prior, cudaStream_t s,
+                    bool inline_ops) {
+  Plan* p = ctx->plan.get();
+  const int B = p->B;
+  const size_t n = static_cast<size_t>(B) * kImage * p->T;
+  const std::vector<float> ev = evaluation_times(ts, N, solver);
+  const int E = static_cast<int>(ev.size());
+  const size_t table_floats = static_cast<size_t>(B) * ctx->dense_rows;
+  int e = 0;                                     // index of the next evaluation
+  // time embeddings of up to kMaxEvals evaluations per launch pair, then one 4*B*R-byte copy per evaluation
+  auto begin_eval = [&](float t, float step) -> int {
+    if (e >= E || ev[e] != t) { ctx->err = "internal: evaluation schedule mismatch"; return 3; }
+    if (e % kMaxEvals == 0) {
+      const int cnt = std::min(kMaxEvals, E - e);
+      launch_set_times(p->t_all, B, ev.data() + e, cnt, s);
+      if (int rc = p->temb_fn(p->t_all, cnt * B, p->bias_all, s)) return rc;
+    }
+    CK(cudaMemcpyAsync(p->bias_table, p->bias_all + static_cast<size_t>(e % kMaxEvals) * table_floats,
+                       table_floats * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    ++e;
+    return set_t(ctx, t, step, s);
+  };
+  launch_prior(own_prior ? p->yp : p->y, p->z, sigma, p->x, n, s);         // x_T = y_prior + sigma z
+  for (int i = 0; i < N; ++i) {
+    const float t = ts[i];
+    const float step = (i != N - 1) ? (t - ts[i + 1]) : ts[N - 1];        // fp32, as sampling/__init__.py:50-53
+    const bool last = (i == N - 1);
+    if (int rc = begin_eval(t, step)) return rc;
+    if (solver == FLOWSE_SOLVER_EULER || last) {
+      if (int rc = run_backbone(ctx, s, inline_ops)) return rc;
+      final_op(ctx, 2, p->x, p->x, s);                                      // x += step * dnn(x, y, t)
+    } else if (solver == FLOWSE_SOLVER_HEUN) {
+      // v0 = VF(x,t); x_next = x + dt v0; x = x + dt/2 (v0 + VF(x_next, t+dt)),  dt = -step, VF = -dnn
+      const float dt = -step;
+      if (int rc = run_backbone(ctx, s, inline_ops)) return rc;
+      final_op(ctx, 1, nullptr, p->va, s);                                  // va = v0
+      CK(cudaMemcpyAsync(p->xa, p->x, n * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+      launch_axpy_c(p->xa, p->va, dt, p->x, n, s);                          // x := x_next (network input)
+      if (int rc = begin_eval(t + dt, step)) return rc;
+      if (int rc = run_backbone(ctx, s, inline_ops)) return rc;
+      final_op(ctx, 1, nullptr, p->vb, s);                                  // vb = VF(x_next, t+dt)
+      launch_heun_combine(p->xa, p->va, p->vb, dt / 2, p->x, n, s);
+    } else {
+      // x = x + dt VF(x + dt/2 VF(x,t), t + dt/2)
+      const float dt = -step;
+      if (int rc = run_backbone(ctx, s, inline_ops)) return rc;
+      final_op(ctx, 1, nullptr, p->va, s);
+      CK(cudaMemcpyAsync(p->xa, p->x, n * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+      launch_axpy_c(p->xa, p->va, dt / 2, p->x, n, s);
+      if (int rc = begin_eval(t + dt / 2, step)) return rc;
+      if (int rc = run_backbone(ctx, s, inline_ops)) return rc;
+      final_op(ctx, 1, nullptr, p->vb, s);
+      launch_axpy_c(p->xa, p->vb, dt, p->x, n, s);
+    }
+  }
+  return 0;
+}
+
+constexpr int kWholeGraphMaxEvals = 12;      // ~240 kernel nodes per evaluation: keep instantiation in the low milliseconds
+constexpr size_t kMaxSamplerGraphs = 4;
+
+}  // namespace
+
+extern "C" {
 
 int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const void* z, const float* ts, int N, int solver, float sigma,
                   void* x_out, int B, int T, void* stream) {
@@ -785,47 +921,70 @@ int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const voi
   if (solver < 0 || solver > 2) { ctx->err = "ODEsolver unknown (0 euler, 1 heun, 2 midpoint)"; return 2; }
   for (int i = 0; i < N; ++i)
     if (!(ts[i] > 0.f)) { ctx->err = "sample: timesteps must be > 0 (the backbone takes log t and divides by t)"; return 2; }
-  if (int rc = ensure_plan(ctx, B, T)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = ensure_plan(ctx, B, T, s)) return rc;
   Plan* p = ctx->plan.get();
   const size_t n = static_cast<size_t>(B) * kImage * T;
+  const bool own_prior = y_prior != nullptr && y_prior != y;
   CK(cudaMemcpyAsync(p->y, y, n * sizeof(float2), cudaMemcpyDeviceToDevice, s));
-  launch_prior(y_prior ? static_cast<const float2*>(y_prior) : p->y, static_cast<const float2*>(z), sigma, p->x, n,
-               s);                                                          // x_T = y_prior + sigma z
-  for (int i = 0; i < N; ++i) {
-    const float t = ts[i];
-    const float step = (i != N - 1) ? (t - ts[i + 1]) : ts[N - 1];        // fp32, as sampling/__init__.py:50-53
-    const bool last = (i == N - 1);
-    if (int rc = set_t(ctx, t, step, s)) return rc;
-    if (solver == FLOWSE_SOLVER_EULER || last) {
-      if (int rc = run_backbone(ctx, s)) return rc;
-      final_op(ctx, 2, p->x, p->x, s);                                      // x += step * dnn(x, y, t)
-    } else if (solver == FLOWSE_SOLVER_HEUN) {
-      // v0 = VF(x,t); x_next = x + dt v0; x = x + dt/2 (v0 + VF(x_next, t+dt)),  dt = -step, VF = -dnn
-      const float dt = -step;
-      if (int rc = run_backbone(ctx, s)) return rc;
-      final_op(ctx, 1, nullptr, p->va, s);                                  // va = v0
-      CK(cudaMemcpyAsync(p->xa, p->x, n * sizeof(float2), cudaMemcpyDeviceToDevice, s));
-      launch_axpy_c(p->xa, p->va, dt, p->x, n, s);                          // x := x_next (network input)
-      if (int rc = set_t(ctx, t + dt, step, s)) return rc;
-      if (int rc = run_backbone(ctx, s)) return rc;
-      final_op(ctx, 1, nullptr, p->vb, s);                                  // vb = VF(x_next, t+dt)
-      launch_heun_combine(p->xa, p->va, p->vb, dt / 2, p->x, n, s);
+  CK(cudaMemcpyAsync(p->z, z, n * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+  if (own_prior) CK(cudaMemcpyAsync(p->yp, y_prior, n * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+
+  // Whole call as ONE graph launch: the second call with a given (schedule, solver, sigma) on a warm plan captures
+  // prior + every evaluation + the fused updates; later calls replay it.
+  const int E = (solver == FLOWSE_SOLVER_EULER) ? N : 2 * N - 1;
+  bool done = false;
+  if (ctx->use_graph && ctx->whole_graph && p->eager_runs >= 1 && E <= kWholeGraphMaxEvals) {
+    Plan::SamplerGraph* g = nullptr;
+    for (auto& c : p->sampler_graphs)
+      if (c.solver == solver && c.sigma == sigma && c.own_prior == own_prior && static_cast<int>(c.ts.size()) == N &&
+          std::memcmp(c.ts.data(), ts, sizeof(float) * N) == 0) { g = &c; break; }
+    if (!g) {
+      if (p->sampler_graphs.size() >= kMaxSamplerGraphs) {
+        if (p->sampler_graphs.front().exec) cudaGraphExecDestroy(p->sampler_graphs.front().exec);
+        p->sampler_graphs.erase(p->sampler_graphs.begin());
+      }
+      p->sampler_graphs.push_back(Plan::SamplerGraph{std::vector<float>(ts, ts + N), solver, sigma, own_prior, nullptr, 0, 1});
     } else {
-      // x = x + dt VF(x + dt/2 VF(x,t), t + dt/2)
-      const float dt = -step;
-      if (int rc = run_backbone(ctx, s)) return rc;
-      final_op(ctx, 1, nullptr, p->va, s);
-      CK(cudaMemcpyAsync(p->xa, p->x, n * sizeof(float2), cudaMemcpyDeviceToDevice, s));
-      launch_axpy_c(p->xa, p->va, dt / 2, p->x, n, s);
-      if (int rc = set_t(ctx, t + dt / 2, step, s)) return rc;
-      if (int rc = run_backbone(ctx, s)) return rc;
-      final_op(ctx, 1, nullptr, p->vb, s);
-      launch_axpy_c(p->xa, p->vb, dt, p->x, n, s);
+      if (!g->exec) {
+        cudaGraph_t cg = nullptr;
+        if (!ctx->cap_stream) CK(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+        CK(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const long long c0 = launch_counter();
+        const int rc = enqueue_sampler(ctx, ts, N, solver, sigma, own_prior, ctx->cap_stream, true);
+        g->kernels = launch_counter() - c0;
+        ctx->counter_base += g->kernels;              // captured, not executed
+        cudaError_t ce = cudaStreamEndCapture(ctx->cap_stream, &cg);
+        if (rc) { if (cg) cudaGraphDestroy(cg); return rc; }
+        if (ce != cudaSuccess) { ctx->err = std::string("sampler graph capture: ") + cudaGetErrorString(ce); return 1; }
+        ce = cudaGraphInstantiate(&g->exec, cg, 0);
+        cudaGraphDestroy(cg);
+        if (ce != cudaSuccess) { g->exec = nullptr; ctx->err = std::string("sampler graph instantiate: ") + cudaGetErrorString(ce); return 1; }
+      }
+      CK(cudaGraphLaunch(g->exec, s));
+      ctx->graph_kernels += g->kernels;
+      done = true;
     }
   }
+  if (!done)
+    if (int rc = enqueue_sampler(ctx, ts, N, solver, sigma, own_prior, s, false)) return rc;
   CK(cudaMemcpyAsync(x_out, p->x, n * sizeof(float2), cudaMemcpyDeviceToDevice, s));
   CK(cudaGetLastError());
+  return 0;
+}
+
+int flowse_fp16_overflow(flowse_ctx* ctx, long long* count, int reset) {
+  if (!ctx) return 2;
+  ctx->err.clear();
+  if (!count) { ctx->err = "fp16_overflow: null count"; return 2; }
+  *count = 0;
+  if (!ctx->overflow) return 0;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  unsigned long long v = 0;
+  CK(cudaMemcpy(&v, ctx->overflow, sizeof(v), cudaMemcpyDeviceToHost));
+  *count = static_cast<long long>(v);
+  if (reset) CK(cudaMemset(ctx->overflow, 0, sizeof(v)));
   return 0;
 }
 
@@ -871,12 +1030,12 @@ int flowse_set_option(flowse_ctx* ctx, const char* key, int value) {
   if (k == "conv_impl") ctx->conv_impl = value;
   else if (k == "graph") ctx->use_graph = value;
   else if (k == "pdl") pdl_mode() = static_cast<int>(value);
+  else if (k == "whole_graph") ctx->whole_graph = value;
   else { ctx->err = "unknown option '" + k + "'"; return 2; }
   if (ctx->plan) {   // captured graphs bake the old setting
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    if (ctx->plan->graph_fwd) { cudaGraphExecDestroy(ctx->plan->graph_fwd); ctx->plan->graph_fwd = nullptr; }
-    ctx->plan->graph_ready = false;
+    destroy_graphs(ctx->plan.get());
   }
   return 0;
 }
@@ -942,6 +1101,7 @@ int flowse_op_gn_prep(flowse_ctx* ctx, const float* src1, int C1, const float* s
   pa.src1 = src1; pa.C1 = C1; pa.src2 = src2; pa.C2 = C2; pa.qs1 = ctx->op_stats; pa.qs2 = qs2; pa.gamma = gamma; pa.beta = beta;
   pa.B = B; pa.H = H; pa.W = W; pa.mode = mode; pa.silu = silu;
   pa.outA = static_cast<__half*>(outA); pa.outX = static_cast<__half*>(outX); pa.outF = outF; pa.outXF = outXF;
+  pa.overflow = ctx->overflow;
   launch_gn_prep(pa, s);
   CK(cudaGetLastError());
   return 0;
@@ -986,6 +1146,7 @@ int stft_prepare(flowse_ctx* ctx, const int* lengths_host, int B, int min_frames
   if (!ctx->stft_basis) {
     CK(cudaMalloc(reinterpret_cast<void**>(&ctx->stft_basis), stft_basis_floats() * sizeof(float)));
     launch_stft_basis(ctx->stft_basis, s);
+    CK(cudaStreamSynchronize(s));      // built once: later calls may come on other streams
   }
   const int Tmax = std::max(stft_frames(Lmax), min_frames);
   const long long xs = ((static_cast<long long>(Lmax) + 510 + 128 + 127) / 128) * 128;
@@ -1039,6 +1200,21 @@ int flowse_spec_istft(flowse_ctx* ctx, const void* X, int Tpad, const int* lengt
   if (!(spec_factor > 0.f) || !(abs_exponent > 0.f)) { ctx->err = "spec_istft: spec_factor and abs_exponent must be > 0"; return 2; }
   launch_spec_istft(ctx->stft_basis, static_cast<const float2*>(X), Tpad, sc.lengths, B, Lmax, spec_factor, abs_exponent, peak,
                     sc.S, sc.frames, wav_out, wav_stride, s);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int flowse_op_head_conv(flowse_ctx* ctx, const float* h, const float* gamma, const float* beta, const float* wf,
+                        const float* bias, const void* prev, void* out, int B, int H, int W, int C, void* stream) {
+  if (!ctx) return 2;
+  ctx->err.clear();
+  if (C % 128 != 0 || C > 256 || B > 64) { ctx->err = "head_conv op: C in {128, 256}, B <= 64"; return 2; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = ensure_op_stats(ctx)) return rc;
+  CK(cudaMemsetAsync(ctx->op_stats, 0, 2 * 64 * kStatSlotDoubles * sizeof(double), s));
+  launch_quad_stats(h, C, B, H * W, ctx->op_stats, ctx->op_partials, ctx->op_counters, s);
+  launch_head_conv(h, ctx->op_stats, gamma, beta, wf, bias, static_cast<const float4*>(prev), static_cast<float4*>(out), B, H,
+                   W, C, s);
   CK(cudaGetLastError());
   return 0;
 }

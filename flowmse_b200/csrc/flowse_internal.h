@@ -70,6 +70,8 @@ void launch_heun_combine(const float2* x, const float2* v0, const float2* v1, fl
 
 // t_dev[0..B) = t; step_dev[0] = step (scalars passed as kernel arguments)
 void launch_set_scalars(float* t_dev, int B, float t, float* step_dev, float step, cudaStream_t s);
+// t_all[e*B + b] = times[e] for e < count <= 64 (the evaluation times of a sampler call, passed by value)
+void launch_set_times(float* t_all, int B, const float* times_host, int count, cudaStream_t s);
 
 struct TembWeights {
   const float* fourier_W;   // [128]
@@ -128,6 +130,7 @@ struct PrepArgs {
   __half* outX;                   // [2][B][Ho][Wo][C] fp16 hi/lo split of (resampled) raw x (may be null)
   float* outF;                    // [B][Ho][Wo][C] fp32 act(GN(x)) (may be null)
   float* outXF;                   // [B][Ho][Wo][C] fp32 resampled raw x (may be null)
+  unsigned long long* overflow;   // optional: counts operand values outside the fp16 hi/lo range (|v| > 65504)
 };
 void launch_gn_prep(const PrepArgs& a, cudaStream_t s);
 

@@ -43,6 +43,12 @@ __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
   lo.x = pack_h2_sat(v.x - f01.x, v.y - f01.y); lo.y = pack_h2_sat(v.z - f23.x, v.w - f23.y);
 }
 __device__ __forceinline__ uint4 pack8(const uint2 a, const uint2 b) { return make_uint4(a.x, a.y, b.x, b.y); }
+// largest magnitude of an operand vector: anything above 65504 saturates in the fp16 hi/lo split, which the kernels
+// report through the context's sticky overflow counter (flowse_fp16_overflow) instead of clipping silently
+__device__ __forceinline__ float amax4(const float4 v, float m) {
+  return fmaxf(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))), m);
+}
+constexpr float kHalfMax = 65504.0f;
 
 // ---------------------------------------------------------------------------------------------
 // "Quad statistics": per (batch, 4-channel quad) sum and sum of squares in double.  Any GroupNorm grouping whose group
@@ -133,6 +139,7 @@ struct PrepK {
   const float* gamma; const float* beta;
   int H, W, Ho, Wo, mode, silu, B;
   __half* outA; __half* outX; float* outF; float* outXF;
+  unsigned long long* overflow;
 };
 
 __device__ __forceinline__ float4 norm_act(const float4 x, const float4 sc, const float4 sh, int silu) {
@@ -239,6 +246,8 @@ gn_prep_plain_kernel(const PrepK k) {
   const size_t obase = static_cast<size_t>(b) * npix * C + c;
   const size_t plane = static_cast<size_t>(k.B) * npix * C;
 
+  float vmax = 0.f;                       // largest operand magnitude this thread split to fp16
+  auto finish = [&]() { if (vmax > kHalfMax && k.overflow) atomicAdd(k.overflow, 1ull); };
   auto emit = [&](int pi, const float4 a0, const float4 a1) {
     const float4 y0 = norm_act(a0, sc0, sh0, k.silu);
     const float4 y1 = norm_act(a1, sc1, sh1, k.silu);
@@ -246,12 +255,14 @@ gn_prep_plain_kernel(const PrepK k) {
     if (k.outA) {
       uint2 h0, l0, h1, l1;
       split4(y0, h0, l0); split4(y1, h1, l1);
+      vmax = amax4(y0, amax4(y1, vmax));
       *reinterpret_cast<uint4*>(k.outA + o) = pack8(h0, h1);
       *reinterpret_cast<uint4*>(k.outA + plane + o) = pack8(l0, l1);
     }
     if (k.outX) {
       uint2 h0, l0, h1, l1;
       split4(a0, h0, l0); split4(a1, h1, l1);
+      vmax = amax4(a0, amax4(a1, vmax));
       *reinterpret_cast<uint4*>(k.outX + o) = pack8(h0, h1);
       *reinterpret_cast<uint4*>(k.outX + plane + o) = pack8(l0, l1);
     }
@@ -260,7 +271,7 @@ gn_prep_plain_kernel(const PrepK k) {
   };
 
   emit(p, x0, x1);
-  if (!has_two) return;
+  if (!has_two) { finish(); return; }
   emit(p + stride, z0, z1);
   p += 2 * stride;
   for (; p + stride < npix; p += 2 * stride) {
@@ -275,6 +286,7 @@ gn_prep_plain_kernel(const PrepK k) {
     const float* a = src + static_cast<size_t>(p) * ld;
     emit(p, __ldg(reinterpret_cast<const float4*>(a)), __ldg(reinterpret_cast<const float4*>(a + 4)));
   }
+  finish();
 }
 
 // FIR down / up x2 fused with the normalisation (single-source inputs only).
@@ -333,6 +345,7 @@ gn_prep_resample_kernel(const PrepK k) {
   }
   __syncthreads();
   const size_t plane = static_cast<size_t>(k.B) * k.Ho * k.Wo * C;
+  float vmax = 0.f;
   for (int op = tid / L; op < TOH * TOW; op += 256 / L) {
     const int oy = op / TOW, ox = op - oy * TOW;
     const int ho = oh0 + oy, wo = ow0 + ox;
@@ -372,18 +385,21 @@ gn_prep_resample_kernel(const PrepK k) {
     if (k.outA) {
       uint2 hi, lo;
       split4(ya, hi, lo);
+      vmax = amax4(ya, vmax);
       *reinterpret_cast<uint2*>(k.outA + o) = hi;
       *reinterpret_cast<uint2*>(k.outA + plane + o) = lo;
     }
     if (k.outX) {
       uint2 hi, lo;
       split4(xa, hi, lo);
+      vmax = amax4(xa, vmax);
       *reinterpret_cast<uint2*>(k.outX + o) = hi;
       *reinterpret_cast<uint2*>(k.outX + plane + o) = lo;
     }
     if (k.outF) *reinterpret_cast<float4*>(k.outF + o) = ya;
     if (k.outXF) *reinterpret_cast<float4*>(k.outXF + o) = xa;
   }
+  if (vmax > kHalfMax && k.overflow) atomicAdd(k.overflow, 1ull);
 }
 
 
@@ -611,7 +627,7 @@ void launch_gn_prep(const PrepArgs& a, cudaStream_t s) {
   k.H = a.H; k.W = a.W; k.mode = a.mode; k.silu = a.silu; k.B = a.B;
   k.Ho = a.mode == kPrepDown ? a.H / 2 : (a.mode == kPrepUp ? a.H * 2 : a.H);
   k.Wo = a.mode == kPrepDown ? a.W / 2 : (a.mode == kPrepUp ? a.W * 2 : a.W);
-  k.outA = a.outA; k.outX = a.outX; k.outF = a.outF; k.outXF = a.outXF;
+  k.outA = a.outA; k.outX = a.outX; k.outF = a.outF; k.outXF = a.outXF; k.overflow = a.overflow;
   const int C = k.C1 + k.C2;
   const int nout = k.Ho * k.Wo;
   const int per_thread = (a.mode == kPrepPlain) ? 8 : 4;

@@ -88,6 +88,14 @@ __global__ void set_scalars_kernel(float* t_dev, int B, float t, float* step_dev
   if (i == 0) step_dev[0] = step;
 }
 
+struct TimeList { float t[64]; };
+__global__ void set_times_kernel(float* t_all, int B, int count, const TimeList tl) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * count) t_all[i] = tl.t[i / B];
+}
+
 inline unsigned grid_for(size_t n, int per_block = 256, unsigned cap = 148 * 8) {
   size_t b = (n + per_block - 1) / per_block;
   if (b < 1) b = 1;
@@ -417,6 +425,12 @@ softmax_rows_kernel(float* __restrict__ s, int rows, int cols) {
 
 void launch_set_scalars(float* t_dev, int B, float t, float* step_dev, float step, cudaStream_t s) {
   launch_k(set_scalars_kernel, dim3((B + 127) / 128), dim3(128), 0, s, t_dev, B, t, step_dev, step);
+}
+
+void launch_set_times(float* t_all, int B, const float* times_host, int count, cudaStream_t s) {
+  TimeList tl{};
+  for (int i = 0; i < count && i < 64; ++i) tl.t[i] = times_host[i];
+  launch_k(set_times_kernel, dim3((B * count + 127) / 128), dim3(128), 0, s, t_all, B, count, tl);
 }
 
 void launch_prior(const float2* y, const float2* z, float sigma, float2* x, size_t n, cudaStream_t s) {

@@ -43,21 +43,17 @@ SR = 16000
 # ---------------------------------------------------------------------------------------------------------------
 # metrics (utils.py:10-36) and the small helpers evaluate.py imports from utils.py
 # ---------------------------------------------------------------------------------------------------------------
-def si_sdr_components(s_hat, s, n):
-    alpha_s = np.dot(s_hat, s) / np.linalg.norm(s) ** 2
-    s_target = alpha_s * s
-    alpha_n = np.dot(s_hat, n) / np.linalg.norm(n) ** 2
-    e_noise = alpha_n * n
-    e_art = s_hat - s_target - e_noise
-    return s_target, e_noise, e_art
-
-
 def energy_ratios(s_hat, s, n):
-    s_target, e_noise, e_art = si_sdr_components(s_hat, s, n)
-    si_sdr = 10 * np.log10(np.linalg.norm(s_target) ** 2 / np.linalg.norm(e_noise + e_art) ** 2)
-    si_sir = 10 * np.log10(np.linalg.norm(s_target) ** 2 / np.linalg.norm(e_noise) ** 2)
-    si_sar = 10 * np.log10(np.linalg.norm(s_target) ** 2 / np.linalg.norm(e_art) ** 2)
-    return si_sdr, si_sir, si_sar
+    """Scale-invariant SDR / SIR / SAR in dB (Le Roux et al. 2019; same decomposition as the reference's utils.py:10-36):
+    the estimate is projected onto the clean signal ``s`` and onto the noise ``n``; what is left is the artefact term."""
+    s_hat, s, n = (np.asarray(v, dtype=np.float64) for v in (s_hat, s, n))
+    target = s * (s_hat @ s / (s @ s))
+    noise = n * (s_hat @ n / (n @ n))
+    artefact = s_hat - target - noise
+    energy = lambda v: float(v @ v)
+    db = lambda num, den: 10.0 * np.log10(num / den)
+    e_t = energy(target)
+    return db(e_t, energy(noise + artefact)), db(e_t, energy(noise)), db(e_t, energy(artefact))
 
 
 def print_mean_std(data, decimals=2):
@@ -221,8 +217,9 @@ def main(argv=None) -> Dict[str, float]:
         from .model import VFModel
         if rank == 0:
             blob = flatten_state_dict(model.dnn.state_dict()).to(dev)
+            # every hyper-parameter the enhancement depends on: all ranks must apply the same STFT / transform
             hp = [dict(t_eps=model.t_eps, T_rev=model.T_rev, sigma_min=model.ode.sigma_min, sigma_max=model.ode.sigma_max,
-                       spec_factor=model.data_module.spec_factor, spec_abs_exponent=model.data_module.spec_abs_exponent)]
+                       **model.data_module.hparams())]
         else:
             blob = torch.empty(ncsnpp_spec.num_params(), dtype=torch.float32, device=dev)
             hp = [None]

@@ -57,6 +57,8 @@ def load_library():
     lib.flowse_op_conv_gemm.argtypes = [vp, vp, i, i, vp, i, vp, i, i, vp, i, vp, i, vp, i, i, i, i, i, i, vp]
     lib.flowse_op_conv_gemm.restype = i
     lib.flowse_op_attention.argtypes = [vp, i, vp, vp, i, i, i, vp]; lib.flowse_op_attention.restype = i
+    lib.flowse_op_head_conv.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp]; lib.flowse_op_head_conv.restype = i
+    lib.flowse_fp16_overflow.argtypes = [vp, C.POINTER(ll), i]; lib.flowse_fp16_overflow.restype = i
     lib.flowse_stft_spec.argtypes = [vp, vp, ll, C.POINTER(i), i, i, f, f, vp, i, vp, vp]; lib.flowse_stft_spec.restype = i
     lib.flowse_spec_istft.argtypes = [vp, vp, i, C.POINTER(i), i, f, f, vp, vp, ll, vp]; lib.flowse_spec_istft.restype = i
     _lib = lib
@@ -67,7 +69,8 @@ EXPORTED_SYMBOLS = [
     "flowse_create", "flowse_destroy", "flowse_last_error", "flowse_load_weights", "flowse_workspace_bytes",
     "flowse_prior_sample", "flowse_ncsnpp_forward", "flowse_euler_step", "flowse_sample", "flowse_set_option",
     "flowse_kernel_launches", "flowse_profile_forward", "flowse_debug_tap", "flowse_debug_copy", "flowse_pack_conv_weights", "flowse_op_gn_prep",
-    "flowse_op_conv_gemm", "flowse_op_attention", "flowse_stft_spec", "flowse_spec_istft",
+    "flowse_op_conv_gemm", "flowse_op_attention", "flowse_stft_spec", "flowse_spec_istft", "flowse_op_head_conv",
+    "flowse_fp16_overflow",
 ]
 
 
@@ -136,6 +139,13 @@ class Context:
     def set_option(self, key: str, value: int):
         self._check(self._lib.flowse_set_option(self._h, key.encode(), int(value)))
 
+    def fp16_overflow(self, reset: bool = True) -> int:
+        """Operand values seen outside the fp16 hi/lo range since the last reset (0 = the fp32-parity claim holds).
+        Synchronises the device."""
+        n = C.c_longlong()
+        self._check(self._lib.flowse_fp16_overflow(self._h, C.byref(n), int(reset)))
+        return int(n.value)
+
     def kernel_launches(self) -> int:
         return int(self._lib.flowse_kernel_launches(self._h))
 
@@ -195,11 +205,12 @@ class Context:
         if y_prior is not None:
             self._check_spec(y_prior, "Y_prior")
         B, _, F, T = y.shape
-        ts = timesteps.detach().to(device="cpu", dtype=torch.float32).contiguous()
-        arr = (C.c_float * ts.numel())(*ts.tolist())
+        if isinstance(timesteps, torch.Tensor):              # a device tensor costs a synchronisation here
+            timesteps = timesteps.detach().to(device="cpu", dtype=torch.float32).tolist()
+        arr = (C.c_float * len(timesteps))(*timesteps)
         out = torch.empty_like(y)
-        self._check(self._lib.flowse_sample(self._h, y.data_ptr(), _ptr(y_prior), z.data_ptr(), arr, ts.numel(), int(solver),
-                                            float(sigma), out.data_ptr(), B, T, _stream()))
+        self._check(self._lib.flowse_sample(self._h, y.data_ptr(), _ptr(y_prior), z.data_ptr(), arr, len(timesteps),
+                                            int(solver), float(sigma), out.data_ptr(), B, T, _stream()))
         return out
 
     # ---- STFT / iSTFT either side of the sampler ----------------------------------
@@ -315,6 +326,16 @@ class Context:
         self._check(self._lib.flowse_op_conv_gemm(self._h, A.data_ptr(), Cin, ntaps, _ptr(X), Cin2, Wp.data_ptr(), npad,
                                                   wexp, bias.data_ptr(), bias_bstride, _ptr(residual), int(div_sqrt2),
                                                   out.data_ptr(), cout, cout, B, H, W, impl, _stream()))
+        return out
+
+    def op_head_conv(self, h_nhwc, gamma, beta, weight, bias, prev=None):
+        """Pyramid head on NHWC fp32 h; weight in the reference layout [4, C, 3, 3]; prev NHWC [B,H/2,W/2,4] or None."""
+        B, H, W, Cc = h_nhwc.shape
+        wf = weight.permute(2, 3, 1, 0).reshape(9, Cc, 4).contiguous()          # [tap][C][4]
+        out = torch.empty((B, H, W, 4), dtype=torch.float32, device=h_nhwc.device)
+        self._check(self._lib.flowse_op_head_conv(self._h, h_nhwc.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                                  wf.data_ptr(), bias.data_ptr(), _ptr(prev), out.data_ptr(), B, H, W,
+                                                  Cc, _stream()))
         return out
 
     def op_attention(self, module_idx: int, x_nhwc: torch.Tensor) -> torch.Tensor:

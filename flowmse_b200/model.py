@@ -24,15 +24,25 @@ class SpecTransform:
     """STFT / iSTFT and the amplitude compression of SpecsDataModule (data_module.py:149-175,177-205)."""
 
     def __init__(self, n_fft=510, hop_length=128, spec_factor=0.15, spec_abs_exponent=0.5, transform_type="exponent",
-                 **ignored):
-        self.n_fft, self.hop_length = n_fft, hop_length
+                 window="hann", **ignored):
+        if window not in ("hann", "sqrthann"):                 # get_window, data_module.py:13-19
+            raise NotImplementedError(f"Window type {window} not implemented!")
+        self.n_fft, self.hop_length, self.window = n_fft, hop_length, window
         self.spec_factor, self.spec_abs_exponent, self.transform_type = spec_factor, spec_abs_exponent, transform_type
         self._windows = {}
+
+    def hparams(self):
+        """The constructor arguments, e.g. to rebuild the same transform on another rank."""
+        return dict(n_fft=self.n_fft, hop_length=self.hop_length, spec_factor=self.spec_factor,
+                    spec_abs_exponent=self.spec_abs_exponent, transform_type=self.transform_type, window=self.window)
 
     def _window(self, x):
         w = self._windows.get(x.device)
         if w is None:
-            w = torch.hann_window(self.n_fft, periodic=True).to(x.device)
+            w = torch.hann_window(self.n_fft, periodic=True)
+            if self.window == "sqrthann":
+                w = torch.sqrt(w)
+            w = w.to(x.device)
             self._windows[x.device] = w
         return w
 
@@ -134,7 +144,8 @@ class VFModel(nn.Module):
         hp.pop("data_module_cls", None)
         hp.update({k: v for k, v in override.items() if k not in ("base_dir", "batch_size", "num_workers", "kwargs")})
         allowed = {k: hp[k] for k in ("backbone", "ode", "t_eps", "T_rev", "sigma_min", "sigma_max", "n_fft",
-                                      "hop_length", "spec_factor", "spec_abs_exponent", "transform_type") if k in hp}
+                                      "hop_length", "spec_factor", "spec_abs_exponent", "transform_type", "window")
+                   if k in hp}
         model = cls(**allowed)
         live = ckpt_io.backbone_state_from_checkpoint(ck, use_ema=False)
         model.dnn.load_state_dict(live, strict=True)
@@ -187,7 +198,8 @@ class VFModel(nn.Module):
 
     def _device_stft_ok(self):
         dm = self.data_module
-        return dm.n_fft == 510 and dm.hop_length == 128 and dm.transform_type == "exponent"
+        # the device STFT kernels are specialised to the FlowSE defaults; anything else takes the per-file torch path
+        return (dm.n_fft == 510 and dm.hop_length == 128 and dm.transform_type == "exponent" and dm.window == "hann")
 
     def enhance_batch(self, wavs, N=5, odesolver="euler", normalize=True, **kw):
         """evaluate.py:97-136 for a list of 1-D waveforms of ANY lengths on one CUDA device, without the per-file host

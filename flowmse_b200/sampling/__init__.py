@@ -20,6 +20,21 @@ def timesteps_and_stepsizes(N, T_rev=1.0, t_eps=0.03, device="cpu"):
     return timesteps, torch.stack(steps)
 
 
+_schedule_cache = {}
+
+
+def _host_schedule(T_rev, t_eps, N, device):
+    """Host copy (tuple of fp32 values) of ``torch.linspace(T_rev, t_eps, N, device=device)`` - the tensor the reference
+    builds on Y's device (sampling/__init__.py:45).  Reading it back is a device synchronisation, so it is done once per
+    distinct (T_rev, t_eps, N, device type) and cached: repeated sampler() calls stay sync-free."""
+    key = (float(T_rev), float(t_eps), int(N), torch.device(device).type)
+    ts = _schedule_cache.get(key)
+    if ts is None:
+        ts = tuple(torch.linspace(T_rev, t_eps, N, device=device).cpu().tolist())
+        _schedule_cache[key] = ts
+    return ts
+
+
 def _fused_backend(VF_fn):
     """The object owning a libflowse context if VF_fn is the B200 vector field, else None."""
     return VF_fn if getattr(VF_fn, "_flowse_fused", False) else None
@@ -34,13 +49,14 @@ def get_white_box_solver(odesolver_name, ode, VF_fn, Y, Y_prior=None, T_rev=1.0,
         with torch.no_grad():
             if Y_prior is None:
                 Y_prior = Y
-            timesteps = torch.linspace(T_rev, t_eps, N, device=Y.device)
             if fused is not None and odesolver_cls.solver_id is not None and Y_prior.shape == Y.shape:
                 z = torch.randn_like(Y_prior)                 # same generator call as ode.prior_sampling
-                x = fused.flowse_context(Y.device).sample(Y.contiguous(), z, timesteps.cpu(),
+                ts = _host_schedule(T_rev, t_eps, N, Y.device)
+                x = fused.flowse_context(Y.device).sample(Y.contiguous(), z, ts,
                                                           solver=odesolver_cls.solver_id, sigma=ode.prior_std(),
                                                           y_prior=None if Y_prior is Y else Y_prior.contiguous())
-                return x, len(timesteps)
+                return x, len(ts)
+            timesteps = torch.linspace(T_rev, t_eps, N, device=Y.device)
             xt, _ = ode.prior_sampling(Y_prior.shape, Y_prior)
             xt = xt.to(Y_prior.device)
             last_euler = ODEsolverRegistry.get_by_name("euler")(ode, VF_fn)

@@ -75,10 +75,18 @@ int flowse_euler_step(flowse_ctx* ctx, const void* x, const void* v, float steps
 int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const void* z, const float* timesteps_host, int N, int solver,
                   float sigma, void* x_out, int B, int T, void* stream);
 
+/* Sticky fp16-range flag.  Conv operands travel as fp16 hi/lo pairs (5 exponent bits): a value with |v| > 65504 - only
+ * possible for the un-normalised shortcut operand of a ResBlock (layerspp.py:268-270) with pathological weights - would
+ * saturate.  The operand-producing kernels count such values; *count receives the number of detections since the last
+ * reset (synchronises the device).  Nothing in the reference corresponds to this: its convolutions are fp32. */
+int flowse_fp16_overflow(flowse_ctx* ctx, long long* count, int reset);
+
 /* Options: "conv_impl" 0 = tcgen05 (default: halo kernel on high-resolution layers, per-tap kernel otherwise),
  * 1 = SIMT cross-check, 2 = per-tap kernel everywhere, 3 = like 0 with 3 rotating main accumulators in the halo kernel,
  * 4 = like 0 with the CTA-pair (cta_group::2) halo kernel; "graph" 0/1 = replay each NFE as a CUDA graph; "pdl" = programmatic dependent launch (process-wide):
- * 0 off, 1 every kernel, 2 (default) the low-resolution conv launches only - the fastest of the three under graph replay. */
+ * 0 off, 1 every kernel, 2 (default) the low-resolution conv launches only - the fastest of the three under graph replay;
+ * "whole_graph" 0/1 (default 1) = flowse_sample replays prior + all evaluations + updates as ONE graph from the second call
+ * with a given schedule. */
 int flowse_set_option(flowse_ctx* ctx, const char* key, int value);
 
 /* Number of this library's kernel launches (graph kernel nodes included) since the context was created. */
@@ -135,6 +143,11 @@ int flowse_op_gn_prep(flowse_ctx* ctx, const float* src1, int C1, const float* s
 int flowse_op_conv_gemm(flowse_ctx* ctx, const void* A, int Cin, int ntaps, const void* X, int Cin2, const void* Wp,
                         int Npad, int wexp, const float* bias, int bias_bstride, const float* residual, int div_sqrt2,
                         float* out, int Cout, int ldc, int B, int H, int W, int impl, void* stream);
+
+/* Pyramid head (ncsnpp.py:347-366): out = FIR-up(prev) + conv3x3(C -> 4)(SiLU(GroupNorm(h))) + bias on NHWC fp32 h
+ * [B,H,W,C]; wf: DEVICE fp32 [9][C][4] (tap-major); prev: [B,H/2,W/2,4] or NULL; out: [B,H,W,4]. */
+int flowse_op_head_conv(flowse_ctx* ctx, const float* h, const float* gamma, const float* beta, const float* wf,
+                        const float* bias, const void* prev, void* out, int B, int H, int W, int C, void* stream);
 
 /* Single-head spatial self-attention block (AttnBlockpp, layerspp.py:62-91) on NHWC fp32 x [B,H,W,256]. */
 int flowse_op_attention(flowse_ctx* ctx, int module_idx, const float* x, float* out, int B, int H, int W, void* stream);
