@@ -24,7 +24,17 @@
 //    Protocol: both CTAs' TMA loads complete on the LEADER's full barriers (cta_group::2 form, leader arms the
 //    transaction count for both), the leader's MMA warp issues for the pair and multicasts its commits to both CTAs'
 //    empty / accumulator-full barriers, both epilogues arrive on the leader's accumulator-empty barrier.
+//  * XF variant (fused operand preparation): 8 extra "transform" warps build the A operand tile in shared memory
+//    themselves.  Per 64-channel chunk they read the fp32 NHWC activations of the halo (virtual concat of two sources),
+//    apply GroupNorm (per-channel scale / shift table assembled from the producers' quad statistics) + SiLU, split to
+//    fp16 hi/lo and store the rows at the SAME swizzled addresses TMA would have written (16-byte column j of row r goes
+//    to r*128 + ((j ^ (r & 7)) << 4)); fence.proxy.async + mbarrier arrive hands the stage to the MMA warp.  The
+//    standalone prep kernel (read 4 B + write 4 B per element, 20 % of an evaluation) is gone for these layers and the
+//    operand values are bit-identical to it.  The shortcut operand (raw x, 1 tap) only needs the 128 centre rows.
+//    Either operand may still come through TMA (after a resampling prep): the producer and the transform warps both
+//    arrive on every stage (count 9), whoever owns the chunk does the work.
 #include "flowse_internal.h"
+#include "operand.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -52,6 +62,10 @@ constexpr int A_SBO = HALO_W * 128;                      // 8-row group g = tile
 constexpr int NUM_THREADS = 384;
 constexpr int kEpiWarps = 8;
 constexpr int kFirstEpiWarp = 4;
+constexpr int kXfWarps = 8;                              // transform warps of the XF variant
+constexpr int kFirstXfWarp = kFirstEpiWarp + kEpiWarps;  // warps 12..19
+constexpr int NUM_THREADS_XF = (kFirstXfWarp + kXfWarps) * 32;   // 640
+constexpr int kXfMaxC = 512;                             // channels of a fused operand (scale / shift table in smem)
 
 template <int BN, int NMAIN, bool PAIR>
 struct HCfg {
@@ -91,6 +105,16 @@ struct HaloParams {
   int div_sqrt2;
   double* qstats;
   long long* dbg;   // optional per-CTA wait-cycle counters (FLOWSE_CONV_DBG=1): 8 per CTA
+};
+
+// fused operand sources (XF variant), device view of FusedOperand
+struct XfOperand { const float* s1; const float* s2; int C1, C2; };
+struct XfParams {
+  XfOperand a, x;                        // main / shortcut operand; s1 == nullptr: that operand comes through TMA
+  const double* qs1; const double* qs2;  // quad statistics of a.s1 / a.s2
+  const float* gamma; const float* beta; // GroupNorm affine of the main operand (over C1 + C2 channels)
+  int silu;
+  unsigned long long* overflow;
 };
 
 struct TileCoord { int b, h0, w0, n0; };
@@ -160,16 +184,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int BN, int NMAIN, bool PAIR>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, int NMAIN, bool PAIR, bool XF>
+__global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX,
-                 const __grid_constant__ CUtensorMap tmW, const HaloParams p) {
+                 const __grid_constant__ CUtensorMap tmW, const HaloParams p, const XfParams xf) {
+  static_assert(!XF || (!PAIR && NMAIN == 1 && BN == 128), "the fused-operand variant exists for the default tile only");
   using C = HCfg<BN, NMAIN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   constexpr int NBARS = 2 * A_STAGES + 2 * C::B_STAGES + 2 * C::NBUF;
   __shared__ uint64_t bars[NBARS];
   __shared__ uint32_t tmem_slot_var;
   __shared__ float s_qs[2][kEpiWarps][C::COLS_PER_WARP / 4 > 0 ? C::COLS_PER_WARP / 4 : 1][2];
+  __shared__ __align__(16) float s_xsc[XF ? kXfMaxC : 4], s_xsh[XF ? kXfMaxC : 4];   // GroupNorm scale / shift per channel
+  __shared__ float s_xmean[kGroups], s_xrstd[kGroups];
 
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = ptx::smem_u32(bars);
@@ -197,7 +224,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmX);
     ptx::prefetch_tensormap(&tmW);
-    for (int s = 0; s < A_STAGES; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
+    // XF: the producer thread and every transform warp arrive on each A stage
+    for (int s = 0; s < A_STAGES; ++s) { ptx::mbar_init(a_full(s), XF ? 1 + kXfWarps : 1); ptx::mbar_init(a_empty(s), 1); }
     for (int s = 0; s < C::B_STAGES; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
     for (int s = 0; s < C::NBUF; ++s) { ptx::mbar_init(t_full(s), 1); ptx::mbar_init(t_empty(s), kEpiWarps * kCtas); }
     ptx::fence_mbar_init();
@@ -224,8 +252,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       auto issue_A = [&](int item, int c) {
         const TileCoord t = decode_tile<BN, PAIR>(p, item, rank);
         { const long long c0 = clock64(); ptx::mbar_wait(a_empty(as), aph ^ 1u); w_pa += clock64() - c0; }
-        if (rank == 0) ptx::mbar_expect_tx(a_full(as), 2 * A_PLANE_BYTES * kCtas);
         const bool main = c < p.nchunk_main;
+        if (XF && (main ? xf.a.s1 : xf.x.s1) != nullptr) {
+          ptx::mbar_arrive(a_full(as));              // the transform warps fill this stage
+          if (++as == A_STAGES) { as = 0; aph ^= 1u; }
+          return;
+        }
+        if (rank == 0) ptx::mbar_expect_tx(a_full(as), 2 * A_PLANE_BYTES * kCtas);
         const CUtensorMap* m = main ? &tmA : &tmX;
         const int ch = main ? c : c - p.nchunk_main;
         const uint32_t bar = full_addr(a_full(as));
@@ -349,6 +382,124 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         p.dbg[blockIdx.x * 8 + 2] = w_a; p.dbg[blockIdx.x * 8 + 3] = w_b;
       }
     }
+  } else if (XF && warp >= kFirstXfWarp) {
+    // ------------------------------------------------------------------ operand transform (warps 12..19, XF only)
+    const int xt = static_cast<int>(threadIdx.x) - kFirstXfWarp * 32;     // 0..255
+    const int j = xt & 7;                      // 16-byte column of the 128-byte operand row: channels 8j .. 8j+7 of the chunk
+    const int r0 = xt >> 3;                    // rows r0 + 32 i
+    int as = 0;
+    uint32_t aph = 0;
+    int cur_b = -1;
+    float vmax = 0.f;
+    const int Ca = xf.a.C1 + xf.a.C2;
+    for (int item = item0; item < p.num_items; item += item_stride) {
+      const TileCoord t = decode_tile<BN, PAIR>(p, item, rank);
+      if (xf.a.s1 != nullptr && xf.gamma != nullptr && t.b != cur_b) {
+        // per-channel scale / shift of this batch element, same arithmetic as the standalone prep (kernels_gn.cu)
+        named_bar_sync(2, kXfWarps * 32);        // nobody still reads the previous table
+        if (xt < kGroups) {
+          const int qpg = (Ca / kGroups) >> 2, q1 = xf.a.C1 >> 2;
+          double su = 0.0, sq = 0.0;
+          for (int jj = 0; jj < qpg; ++jj) {
+            const int qd = xt * qpg + jj;
+#pragma unroll
+            for (int r = 0; r < kStatReplicas; ++r) {
+              const double2 v = (qd < q1)
+                  ? reinterpret_cast<const double2*>(qstat_slot(xf.qs1, t.b, r, q1))[qd]
+                  : reinterpret_cast<const double2*>(qstat_slot(xf.qs2, t.b, r, xf.a.C2 >> 2))[qd - q1];
+              su += v.x; sq += v.y;
+            }
+          }
+          const double n = static_cast<double>(p.H) * p.W * (Ca / kGroups);
+          const double mean = su / n;
+          double var = sq / n - mean * mean;
+          if (var < 0.0) var = 0.0;
+          s_xmean[xt] = static_cast<float>(mean);
+          s_xrstd[xt] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
+        }
+        named_bar_sync(2, kXfWarps * 32);
+        const int cpg = Ca / kGroups;
+        for (int c = xt; c < Ca; c += kXfWarps * 32) {
+          const int g = c / cpg;
+          const float sc = s_xrstd[g] * __ldg(xf.gamma + c);
+          s_xsc[c] = sc;
+          s_xsh[c] = fmaf(-s_xmean[g], sc, __ldg(xf.beta + c));
+        }
+        named_bar_sync(2, kXfWarps * 32);
+        cur_b = t.b;
+      }
+      for (int c = 0; c < nchunks; ++c) {
+        const bool main = c < p.nchunk_main;
+        const XfOperand& src = main ? xf.a : xf.x;
+        ptx::mbar_wait(a_empty(as), aph ^ 1u);
+        if (src.s1 != nullptr) {
+          const int cg = (main ? c : c - p.nchunk_main) * BK;             // first channel of the chunk in the concat
+          const float* base; int ld;
+          if (cg < src.C1) { base = src.s1 + cg; ld = src.C1; } else { base = src.s2 + (cg - src.C1); ld = src.C2; }
+          base += static_cast<size_t>(t.b) * p.H * p.W * ld + j * 8;
+          const bool norm = main && xf.gamma != nullptr;
+          float4 sc0, sc1, sh0, sh1;
+          if (norm) {
+            sc0 = *reinterpret_cast<const float4*>(s_xsc + cg + j * 8); sc1 = *reinterpret_cast<const float4*>(s_xsc + cg + j * 8 + 4);
+            sh0 = *reinterpret_cast<const float4*>(s_xsh + cg + j * 8); sh1 = *reinterpret_cast<const float4*>(s_xsh + cg + j * 8 + 4);
+          }
+          const uint32_t stage = sA(as);
+          auto emit = [&](int r, bool inb, float4 a0, float4 a1) {
+            uint2 h0 = make_uint2(0u, 0u), l0 = h0, h1 = h0, l1 = h0;
+            if (inb) {
+              if (norm) { a0 = norm_act(a0, sc0, sh0, xf.silu); a1 = norm_act(a1, sc1, sh1, xf.silu); }
+              split4(a0, h0, l0); split4(a1, h1, l1);
+              vmax = amax4(a0, amax4(a1, vmax));
+            }
+            const uint32_t dst = stage + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
+            ptx::st_shared_v4(dst, pack8(h0, h1));
+            ptx::st_shared_v4(dst + A_PLANE_STRIDE, pack8(l0, l1));
+          };
+          if (main) {
+            // all 180 halo rows; loads of 3 rows in flight per thread
+#pragma unroll
+            for (int i0 = 0; i0 < 6; i0 += 3) {
+              float4 v0[3], v1[3]; bool inb[3]; int rr[3];
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                const int r = r0 + 32 * (i0 + i);
+                rr[i] = r;
+                const int hy = r / HALO_W, hx = r - hy * HALO_W;
+                const int h = t.h0 - 1 + hy, w = t.w0 - 1 + hx;
+                inb[i] = r < A_ROWS && h >= 0 && h < p.H && w >= 0 && w < p.W;
+                v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i];
+                if (inb[i]) {
+                  const float4* g = reinterpret_cast<const float4*>(base + (static_cast<size_t>(h) * p.W + w) * ld);
+                  v0[i] = __ldg(g); v1[i] = __ldg(g + 1);
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 3; ++i) if (rr[i] < A_ROWS) emit(rr[i], inb[i], v0[i], v1[i]);
+            }
+          } else {
+            // 1x1 shortcut: the 128 centre rows only (always inside the image)
+            float4 v0[4], v1[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int idx = r0 + 32 * i;
+              const int h = t.h0 + (idx >> 3), w = t.w0 + (idx & 7);
+              const float4* g = reinterpret_cast<const float4*>(base + (static_cast<size_t>(h) * p.W + w) * ld);
+              v0[i] = __ldg(g); v1[i] = __ldg(g + 1);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int idx = r0 + 32 * i;
+              emit(((idx >> 3) + 1) * HALO_W + (idx & 7) + 1, true, v0[i], v1[i]);
+            }
+          }
+          ptx::fence_proxy_async();            // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(a_full(as));
+        if (++as == A_STAGES) { as = 0; aph ^= 1u; }
+      }
+    }
+    if (vmax > kHalfMax && xf.overflow) atomicAdd(xf.overflow, 1ull);
   } else if (warp >= kFirstEpiWarp) {
     // ------------------------------------------------------------------ epilogue (warps 4..11)
     // Two warps per TMEM lane quadrant, each owning half of the tile's columns, CH columns per pass: TMEM -> registers
@@ -544,12 +695,12 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int NMAIN, bool PAIR>
+template <int BN, int NMAIN, bool PAIR, bool XF = false>
 int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   using C = HCfg<BN, NMAIN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, NMAIN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, NMAIN, PAIR, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(halo): ") + cudaGetErrorString(e); return 1; }
     attr_set = true;
@@ -561,19 +712,33 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   const int m_tiles = a.B * p.tiles_w * p.tiles_h;
   p.num_items = (PAIR ? m_tiles / 2 : m_tiles) * p.n_tiles;
   p.nchunk_main = a.Cin / BK;
-  p.nchunk_sc = a.X ? a.Cin2 / BK : 0;
   p.Cout = a.Cout; p.ldc = a.ldc; p.wscale_inv = a.wscale_inv;
   p.bias = a.bias; p.bias_bstride = a.bias_bstride; p.residual = a.residual; p.out = a.out;
   p.div_sqrt2 = a.div_sqrt2; p.qstats = a.qstats;
-  const int K = 9 * a.Cin + (a.X ? a.Cin2 : 0);
+  const bool has_x = a.X != nullptr || a.fX.s1 != nullptr;
+  p.nchunk_sc = has_x ? a.Cin2 / BK : 0;
+  const int K = 9 * a.Cin + (has_x ? a.Cin2 : 0);
+  XfParams xf{};
+  if (XF) {
+    xf.a = XfOperand{a.fA.s1, a.fA.s2, a.fA.C1, a.fA.s2 ? a.fA.C2 : 0};
+    xf.x = XfOperand{a.fX.s1, a.fX.s2, a.fX.C1, a.fX.s2 ? a.fX.C2 : 0};
+    xf.qs1 = a.fA.qs1; xf.qs2 = a.fA.qs2; xf.gamma = a.fA.gamma; xf.beta = a.fA.beta; xf.silu = a.fA.silu;
+    xf.overflow = a.overflow;
+    auto bad = [&](const char* m) { if (err) *err = std::string("conv_halo (fused operand): ") + m; return 1; };
+    if (a.fA.s1 && (xf.a.C1 + xf.a.C2 != a.Cin || xf.a.C1 % BK || a.Cin > kXfMaxC)) return bad("main operand channels");
+    if (a.fA.s1 && a.fA.gamma && (!a.fA.beta || !a.fA.qs1 || (xf.a.C2 && !a.fA.qs2))) return bad("GroupNorm parameters / statistics missing");
+    if (a.fX.s1 && (xf.x.C1 + xf.x.C2 != a.Cin2 || xf.x.C1 % BK)) return bad("shortcut operand channels");
+    if (!a.fA.s1 && !a.A) return bad("no main operand");
+  }
   CUtensorMap tmA, tmX, tmW;
-  if (!make_halo_map(&tmA, a.A, a.B, a.H, a.W, a.Cin, err)) return 1;
-  if (a.X) { if (!make_halo_map(&tmX, a.X, a.B, a.H, a.W, a.Cin2, err)) return 1; }
-  else tmX = tmA;
   if (!make_weight_map(&tmW, a.Wp, a.Npad, K, C::B_ROWS, err)) return 1;
+  if (a.A && !(XF && a.fA.s1)) { if (!make_halo_map(&tmA, a.A, a.B, a.H, a.W, a.Cin, err)) return 1; }
+  else tmA = tmW;                                      // unused: that operand is produced in the kernel
+  if (a.X && !(XF && a.fX.s1)) { if (!make_halo_map(&tmX, a.X, a.B, a.H, a.W, a.Cin2, err)) return 1; }
+  else tmX = tmA;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[2];
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(XF ? NUM_THREADS_XF : NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = s;
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -592,7 +757,7 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   long long* dbuf = nullptr;
   const size_t nctas = cfg.gridDim.x;
   if (dbg) { cudaMalloc(&dbuf, nctas * 8 * sizeof(long long)); cudaMemset(dbuf, 0, nctas * 8 * sizeof(long long)); p.dbg = dbuf; }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, NMAIN, PAIR>, tmA, tmX, tmW, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, NMAIN, PAIR, XF>, tmA, tmX, tmW, p, xf);
   ++launch_counter();
   if (dbg) {
     cudaStreamSynchronize(s);
@@ -618,7 +783,7 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
 }  // namespace
 
 bool conv_halo_supported(const ConvGemmArgs& a) {
-  return a.ntaps == 9 && a.H % TH == 0 && a.W % TW == 0 && a.Cin % BK == 0 && (!a.X || a.Cin2 % BK == 0) &&
+  return a.ntaps == 9 && a.H % TH == 0 && a.W % TW == 0 && a.Cin % BK == 0 && ((!a.X && !a.fX.s1) || a.Cin2 % BK == 0) &&
          (a.Npad % 128 == 0 || a.Npad == 16);
 }
 
@@ -626,6 +791,10 @@ bool conv_halo_supported(const ConvGemmArgs& a) {
 //          2 = CTA pairs (cta_group::2, one main accumulator, double-buffered TMEM); falls back to 1 when unavailable
 int launch_conv_halo(const ConvGemmArgs& a, int variant, cudaStream_t s, std::string* err) {
   if (!conv_halo_supported(a)) { if (err) *err = "conv_halo: unsupported shape"; return 1; }
+  if (a.fA.s1 || a.fX.s1) {
+    if (a.Npad % 128 != 0) { if (err) *err = "conv_halo: fused operands need Cout tiles of 128"; return 1; }
+    return launch_halo<128, 1, false, true>(a, s, err);
+  }
   if (a.Npad % 128 == 0) {
     const int m_tiles = a.B * (a.W / TW) * (a.H / TH);
     if (variant == 2 && m_tiles % 2 == 0) return launch_halo<128, 1, true>(a, s, err);

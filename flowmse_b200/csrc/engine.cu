@@ -11,6 +11,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -194,6 +195,7 @@ struct flowse_ctx {
   // (|v| > 65504 saturates silently otherwise); read back through flowse_fp16_overflow
   unsigned long long* overflow = nullptr;
   int whole_graph = 1;                      // capture the whole sampler call as one CUDA graph (second call with the same schedule)
+  int fuse_prep = 1;                        // halo-kernel layers prepare their operands in the conv kernel (no standalone prep pass)
 };
 
 namespace {
@@ -391,7 +393,7 @@ struct Builder {
     if (!dry) plan->ops.push_back(Op{std::move(fn), nk, kind, flops, {i0, i1, i2, i3}});
   }
   static double conv_flops(const ConvGemmArgs& a) {
-    const double K = static_cast<double>(a.ntaps) * a.Cin + (a.X ? a.Cin2 : 0);
+    const double K = static_cast<double>(a.ntaps) * a.Cin + a.Cin2;      // Cin2 = 0 without a folded shortcut
     return 2.0 * a.B * a.H * a.W * a.Cout * K;
   }
   // one slot = quad statistics of a tensor with up to 256 channels: [B][64][2] doubles
@@ -417,31 +419,58 @@ struct Builder {
     double* st1 = stat_slot();                    // statistics of the Conv_0 output, filled by its epilogue
     const float* s1 = in1.p; const int C1 = in1.C;
     const float* s2 = in2 ? in2->p : nullptr; const int C2 = in2 ? in2->C : 0;
-    PrepArgs pa{};
-    pa.src1 = s1; pa.C1 = C1; pa.src2 = s2; pa.C2 = C2; pa.qs1 = in1.qs; pa.qs2 = in2 ? in2->qs : nullptr;
-    pa.gamma = r.gn0_g; pa.beta = r.gn0_b;
-    pa.B = B; pa.H = H; pa.W = W; pa.mode = r.down ? kPrepDown : (r.up ? kPrepUp : kPrepPlain); pa.silu = 1;
-    pa.outA = scrA; pa.outX = r.has_sc ? scrX : nullptr; pa.overflow = ctx->overflow;
-    push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; }, 2);
+    // conv arguments first: whether a layer runs on the halo kernel decides who prepares its operands
     ConvGemmArgs c0{};
     c0.A = scrA; c0.Cin = Cin; c0.ntaps = 9; c0.X = nullptr; c0.Cin2 = 0; c0.Wp = r.conv0.wp; c0.Npad = r.conv0.Npad;
     c0.wscale_inv = r.conv0.wscale_inv; c0.bias = bias_table + r.dense_off; c0.bias_bstride = ctx->dense_rows;
     c0.residual = nullptr; c0.div_sqrt2 = 0; c0.out = scrH1; c0.Cout = r.cout; c0.ldc = r.cout;
     c0.B = B; c0.H = Ho; c0.W = Wo;
     c0.splitk_scratch = splitk; c0.splitk_scratch_elems = kSplitKScratchElems; c0.qstats = st1;
-    { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c0, s); }, conv_uses_halo(cx, c0) ? 7 : 3, conv_flops(c0), c0.H, c0.W, c0.ntaps * c0.Cin + (c0.X ? c0.Cin2 : 0), c0.Cout); }
+    c0.overflow = ctx->overflow;
     float* h1 = scrH1; const int Co = r.cout;
-    PrepArgs pb{};
-    pb.src1 = h1; pb.C1 = Co; pb.src2 = nullptr; pb.C2 = 0; pb.qs1 = st1; pb.gamma = r.gn1_g; pb.beta = r.gn1_b;
-    pb.B = B; pb.H = Ho; pb.W = Wo; pb.mode = kPrepPlain; pb.silu = 1; pb.outA = scrA; pb.overflow = ctx->overflow;
-    push(1, [=](cudaStream_t s) { launch_gn_prep(pb, s); return 0; }, 2);
     ConvGemmArgs c1{};
     c1.A = scrA; c1.Cin = Co; c1.ntaps = 9; c1.X = r.has_sc ? scrX : nullptr; c1.Cin2 = r.has_sc ? Cin : 0;
     c1.Wp = r.conv1.wp; c1.Npad = r.conv1.Npad; c1.wscale_inv = r.conv1.wscale_inv; c1.bias = r.bias1;
     c1.bias_bstride = 0; c1.residual = r.has_sc ? nullptr : s1; c1.div_sqrt2 = 1; c1.out = out.p; c1.Cout = Co;
     c1.ldc = Co; c1.B = B; c1.H = Ho; c1.W = Wo;
     c1.splitk_scratch = splitk; c1.splitk_scratch_elems = kSplitKScratchElems; c1.qstats = out.qs;
-    { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c1, s); }, conv_uses_halo(cx, c1) ? 7 : 3, conv_flops(c1), c1.H, c1.W, c1.ntaps * c1.Cin + (c1.X ? c1.Cin2 : 0), c1.Cout); }
+    c1.overflow = ctx->overflow;
+    // Fused operand preparation (halo-kernel layers): GroupNorm + SiLU + fp16 split happen in the conv kernel's transform
+    // warps, reading the fp32 activations directly.  A resampling block keeps its FIR prep for Conv_0 and for the shortcut
+    // operand; its Conv_1 still normalises h1 itself.
+    const bool resample = r.up || r.down;
+    const bool fuse0 = ctx->fuse_prep && !resample && conv_uses_halo(ctx, c0) && Cin <= 512;
+    const bool fuse1 = ctx->fuse_prep && conv_uses_halo(ctx, c1) && Co <= 512;
+    if (fuse0) {
+      c0.A = nullptr;
+      c0.fA.s1 = s1; c0.fA.C1 = C1; c0.fA.s2 = s2; c0.fA.C2 = C2; c0.fA.qs1 = in1.qs; c0.fA.qs2 = in2 ? in2->qs : nullptr;
+      c0.fA.gamma = r.gn0_g; c0.fA.beta = r.gn0_b; c0.fA.silu = 1;
+    }
+    if (fuse1) {
+      c1.A = nullptr;
+      c1.fA.s1 = h1; c1.fA.C1 = Co; c1.fA.qs1 = st1; c1.fA.gamma = r.gn1_g; c1.fA.beta = r.gn1_b; c1.fA.silu = 1;
+      if (r.has_sc && !resample) {          // raw block input as the 1x1 shortcut operand
+        c1.X = nullptr;
+        c1.fX.s1 = s1; c1.fX.C1 = C1; c1.fX.s2 = s2; c1.fX.C2 = C2;
+      }
+    }
+    const bool need_x_operand = r.has_sc && !(fuse1 && !resample);
+    if (!fuse0 || need_x_operand) {
+      PrepArgs pa{};
+      pa.src1 = s1; pa.C1 = C1; pa.src2 = s2; pa.C2 = C2; pa.qs1 = in1.qs; pa.qs2 = in2 ? in2->qs : nullptr;
+      pa.gamma = r.gn0_g; pa.beta = r.gn0_b;
+      pa.B = B; pa.H = H; pa.W = W; pa.mode = r.down ? kPrepDown : (r.up ? kPrepUp : kPrepPlain); pa.silu = 1;
+      pa.outA = fuse0 ? nullptr : scrA; pa.outX = need_x_operand ? scrX : nullptr; pa.overflow = ctx->overflow;
+      push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; }, 2);
+    }
+    { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c0, s); }, conv_uses_halo(cx, c0) ? 7 : 3, conv_flops(c0), c0.H, c0.W, c0.ntaps * c0.Cin, c0.Cout); }
+    if (!fuse1) {
+      PrepArgs pb{};
+      pb.src1 = h1; pb.C1 = Co; pb.src2 = nullptr; pb.C2 = 0; pb.qs1 = st1; pb.gamma = r.gn1_g; pb.beta = r.gn1_b;
+      pb.B = B; pb.H = Ho; pb.W = Wo; pb.mode = kPrepPlain; pb.silu = 1; pb.outA = scrA; pb.overflow = ctx->overflow;
+      push(1, [=](cudaStream_t s) { launch_gn_prep(pb, s); return 0; }, 2);
+    }
+    { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c1, s); }, conv_uses_halo(cx, c1) ? 7 : 3, conv_flops(c1), c1.H, c1.W, c1.ntaps * c1.Cin + c1.Cin2, c1.Cout); }
     plan->taps[mi] = out;
     return out;
   }
@@ -731,6 +760,9 @@ int flowse_create(flowse_ctx** out, int device) {
   ctx->device = device;
   ctx->mods = build_modules();
   ctx->counter_base = launch_counter();
+  // A/B switches for measurements (the options of flowse_set_option, preset from the environment)
+  if (const char* e = getenv("FLOWSE_FUSE_PREP")) ctx->fuse_prep = atoi(e);
+  if (const char* e = getenv("FLOWSE_WHOLE_GRAPH")) ctx->whole_graph = atoi(e);
   cudaSetDevice(device);
   if (cudaMalloc(reinterpret_cast<void**>(&ctx->overflow), sizeof(unsigned long long)) != cudaSuccess ||
       cudaMemset(ctx->overflow, 0, sizeof(unsigned long long)) != cudaSuccess) {
@@ -1027,7 +1059,9 @@ int flowse_set_option(flowse_ctx* ctx, const char* key, int value) {
   if (!ctx || !key) return 2;
   ctx->err.clear();
   const std::string k(key);
-  if (k == "conv_impl") ctx->conv_impl = value;
+  bool replan = false;            // the op list depends on the option: rebuild the plan on the next call
+  if (k == "conv_impl") { ctx->conv_impl = value; replan = true; }
+  else if (k == "fuse_prep") { ctx->fuse_prep = value; replan = true; }
   else if (k == "graph") ctx->use_graph = value;
   else if (k == "pdl") pdl_mode() = static_cast<int>(value);
   else if (k == "whole_graph") ctx->whole_graph = value;
@@ -1036,6 +1070,7 @@ int flowse_set_option(flowse_ctx* ctx, const char* key, int value) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     destroy_graphs(ctx->plan.get());
+    if (replan) ctx->plan.reset();
   }
   return 0;
 }

@@ -142,6 +142,18 @@ void launch_head_conv(const float* h, const double* qs, const float* gamma, cons
 // ---------------------------------------------------------------------------------------------
 // Implicit-GEMM convolution on tcgen05 (conv_gemm.cu)
 // ---------------------------------------------------------------------------------------------
+// An operand the conv kernel prepares ITSELF from fp32 NHWC activations (halo kernel only): the virtual channel concat
+// [s1, s2] is normalised (GroupNorm from the producers' quad statistics, affine gamma / beta), activated (SiLU) and split
+// to fp16 hi/lo by transform warps straight into the swizzled shared-memory operand tile - the standalone prep pass
+// (one full read + write of the tensor) disappears.  gamma == nullptr: raw split only (the 1x1 shortcut operand).
+struct FusedOperand {
+  const float* s1 = nullptr; int C1 = 0;
+  const float* s2 = nullptr; int C2 = 0;
+  const double* qs1 = nullptr; const double* qs2 = nullptr;
+  const float* gamma = nullptr; const float* beta = nullptr;
+  int silu = 0;
+};
+
 struct ConvGemmArgs {
   const __half* A;      // [2][B][H][W][Cin]  hi/lo split activations
   int Cin;              // multiple of 64
@@ -162,6 +174,8 @@ struct ConvGemmArgs {
   double* qstats;               // optional: accumulate quad statistics of the OUTPUT (zeroed buffer)
   float* splitk_scratch;        // optional fp32 scratch enabling split-K for low-resolution layers (may be null)
   size_t splitk_scratch_elems;
+  FusedOperand fA, fX;          // halo kernel: prepare the main / shortcut operand in the kernel (s1 != nullptr) instead of A / X
+  unsigned long long* overflow; // optional fp16-range counter for the fused operands
 };
 constexpr size_t kSplitKScratchElems = static_cast<size_t>(148) * 128 * 128;   // enough for any one-wave split
 // returns 0 on success; fills err otherwise.
