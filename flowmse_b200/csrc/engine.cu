@@ -477,44 +477,15 @@ struct Builder {
 
   Act attention(int mi, const Act& in) {
     const AttnW& a = ctx->attns.at(mi);
-    const int C = a.c, H = in.H, W = in.W, L = H * W, Bc = B;
+    const int C = a.c, H = in.H, W = in.W, L = H * W;
     Act out = new_act(C, H, W);
-    double* gp = plan->gn_partials; unsigned* gc = plan->gn_counters;
-    const float* x = in.p;
-    PrepArgs pa{};
-    pa.src1 = x; pa.C1 = C; pa.qs1 = in.qs; pa.gamma = a.gn_g; pa.beta = a.gn_b; pa.B = B; pa.H = H; pa.W = W;
-    pa.mode = kPrepPlain; pa.silu = 0; pa.outF = scrF;
-    push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; }, 2);
-    float *hn = scrF, *qkv = scrQKV, *S = scrS, *O = scrO, *o = out.p;
-    push(1, [=](cudaStream_t s) {   // q,k,v = NIN_0..2(h)
-      SgemmArgs g{}; g.A = hn; g.lda = C; g.Bm = a.wqkv; g.ldb = 3 * C; g.transB = 0; g.C = qkv; g.ldc = 3 * C;
-      g.M = Bc * L; g.N = 3 * C; g.K = C; g.batch = 1; g.alpha = 1.f; g.bias = a.bqkv;
-      launch_sgemm(g, s); return 0; }, 4);
-    push(1, [=](cudaStream_t s) {   // w = q.k^T * C^-0.5
-      SgemmArgs g{}; g.A = qkv; g.lda = 3 * C; g.strideA = static_cast<long long>(L) * 3 * C;
-      g.Bm = qkv + C; g.ldb = 3 * C; g.strideB = g.strideA; g.transB = 1;
-      g.C = S; g.ldc = L; g.strideC = static_cast<long long>(L) * L; g.M = L; g.N = L; g.K = C; g.batch = Bc;
-      g.alpha = 1.0f / sqrtf(static_cast<float>(C));
-      launch_sgemm(g, s); return 0; }, 4);
-    push(1, [=](cudaStream_t s) { launch_softmax_rows(S, Bc * L, L, s); return 0; }, 4);
-    push(1, [=](cudaStream_t s) {   // h = w.v
-      SgemmArgs g{}; g.A = S; g.lda = L; g.strideA = static_cast<long long>(L) * L;
-      g.Bm = qkv + 2 * C; g.ldb = 3 * C; g.strideB = static_cast<long long>(L) * 3 * C; g.transB = 0;
-      g.C = O; g.ldc = C; g.strideC = static_cast<long long>(L) * C; g.M = L; g.N = C; g.K = L; g.batch = Bc;
-      g.alpha = 1.f;
-      launch_sgemm(g, s); return 0; }, 4);
-    // (x + NIN_3(h)) / sqrt(2); the quad statistics of the block output (consumed by the next GroupNorm) are accumulated
-    // in the GEMM epilogue when a row tile never straddles two batch elements, else by the standalone kernel
-    SgemmArgs g3{}; g3.A = O; g3.lda = C; g3.Bm = a.w3; g3.ldb = C; g3.transB = 0; g3.C = o; g3.ldc = C;
-    g3.M = Bc * L; g3.N = C; g3.K = C; g3.batch = 1; g3.alpha = 1.f; g3.bias = a.b3; g3.residual = x; g3.ldr = C;
-    g3.div_sqrt2 = 1;
-    const bool fuse_stats = (L % sgemm_tile_rows(g3)) == 0;
-    if (fuse_stats) { g3.qstats = out.qs; g3.qs_rows_per_batch = L; }
-    push(1, [=](cudaStream_t s) { launch_sgemm(g3, s); return 0; }, 4);
-    if (!fuse_stats) {
-      double* oq = out.qs;
-      push(1, [=](cudaStream_t s) { launch_quad_stats(o, C, Bc, L, oq, gp, gc, s); return 0; }, 1);
-    }
+    AttentionArgs aa{};
+    aa.x = in.p; aa.qs = in.qs; aa.gamma = a.gn_g; aa.beta = a.gn_b; aa.wqkv = a.wqkv; aa.bqkv = a.bqkv; aa.w3 = a.w3;
+    aa.b3 = a.b3; aa.out = out.p; aa.qstats = out.qs; aa.scratch = scrQKV; aa.B = B; aa.L = L; aa.C = C;
+    flowse_ctx* cx = ctx;
+    // GroupNorm + q,k,v = NIN_0..2(h); softmax(q k^T C^-1/2) v; (x + NIN_3(h)) / sqrt(2) + output statistics: 2 kernels
+    push(2, [=](cudaStream_t s) { std::string e; const int rc = launch_attention(aa, s, &e); if (rc) cx->err = e; return rc; }, 4,
+         2.0 * B * L * (4.0 * C * C + 2.0 * L * C));
     plan->taps[mi] = out;
     return out;
   }
@@ -540,10 +511,7 @@ struct Builder {
     scrX = ar.alloc<__half>(2 * top * 256);
     scrH1 = ar.alloc<float>(top * 128);
     const int La = kAttnRes * (T / 16);           // tokens of the 16 x T/16 attention blocks
-    scrF = ar.alloc<float>(static_cast<size_t>(B) * La * 256);
-    scrQKV = ar.alloc<float>(static_cast<size_t>(B) * La * 768);
-    scrS = ar.alloc<float>(static_cast<size_t>(B) * La * La);
-    scrO = ar.alloc<float>(static_cast<size_t>(B) * La * 256);
+    scrQKV = ar.alloc<float>(attention_scratch_floats(B, La));
     splitk = ar.alloc<float>(kSplitKScratchElems);
     plan->stats_bytes = static_cast<size_t>(kMaxStatSlots) * B * kStatSlotDoubles * sizeof(double);
     plan->stats = ar.alloc<double>(plan->stats_bytes / sizeof(double));
@@ -1263,7 +1231,7 @@ int flowse_op_attention(flowse_ctx* ctx, int module_idx, const float* x, float* 
   const AttnW& a = it->second;
   const int C = a.c, L = H * W;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t need = (static_cast<size_t>(B) * L * (C + 3 * C + C) + static_cast<size_t>(B) * L * L) * sizeof(float);
+  const size_t need = attention_scratch_floats(B, L) * sizeof(float);
   if (ctx->op_scratch_bytes < need) {
     CK(cudaDeviceSynchronize());
     if (ctx->op_scratch) cudaFree(ctx->op_scratch);
@@ -1272,35 +1240,13 @@ int flowse_op_attention(flowse_ctx* ctx, int module_idx, const float* x, float* 
   }
   if (B > 64) { ctx->err = "attention op: B <= 64"; return 2; }
   if (int rc = ensure_op_stats(ctx)) return rc;
-  float* hn = ctx->op_scratch;
-  float* qkv = hn + static_cast<size_t>(B) * L * C;
-  float* O = qkv + static_cast<size_t>(B) * L * 3 * C;
-  float* S = O + static_cast<size_t>(B) * L * C;
   CK(cudaMemsetAsync(ctx->op_stats, 0, 2 * 64 * kStatSlotDoubles * sizeof(double), s));
   launch_quad_stats(x, C, B, L, ctx->op_stats, ctx->op_partials, ctx->op_counters, s);
-  PrepArgs pa{};
-  pa.src1 = x; pa.C1 = C; pa.qs1 = ctx->op_stats; pa.gamma = a.gn_g; pa.beta = a.gn_b; pa.B = B; pa.H = H; pa.W = W;
-  pa.mode = kPrepPlain; pa.silu = 0; pa.outF = hn;
-  launch_gn_prep(pa, s);
-  SgemmArgs g{};
-  g.A = hn; g.lda = C; g.Bm = a.wqkv; g.ldb = 3 * C; g.C = qkv; g.ldc = 3 * C; g.M = B * L; g.N = 3 * C; g.K = C;
-  g.batch = 1; g.alpha = 1.f; g.bias = a.bqkv;
-  launch_sgemm(g, s);
-  g = SgemmArgs{};
-  g.A = qkv; g.lda = 3 * C; g.strideA = static_cast<long long>(L) * 3 * C; g.Bm = qkv + C; g.ldb = 3 * C;
-  g.strideB = g.strideA; g.transB = 1; g.C = S; g.ldc = L; g.strideC = static_cast<long long>(L) * L;
-  g.M = L; g.N = L; g.K = C; g.batch = B; g.alpha = 1.0f / sqrtf(static_cast<float>(C));
-  launch_sgemm(g, s);
-  launch_softmax_rows(S, B * L, L, s);
-  g = SgemmArgs{};
-  g.A = S; g.lda = L; g.strideA = static_cast<long long>(L) * L; g.Bm = qkv + 2 * C; g.ldb = 3 * C;
-  g.strideB = static_cast<long long>(L) * 3 * C; g.C = O; g.ldc = C; g.strideC = static_cast<long long>(L) * C;
-  g.M = L; g.N = C; g.K = L; g.batch = B; g.alpha = 1.f;
-  launch_sgemm(g, s);
-  g = SgemmArgs{};
-  g.A = O; g.lda = C; g.Bm = a.w3; g.ldb = C; g.C = out; g.ldc = C; g.M = B * L; g.N = C; g.K = C; g.batch = 1;
-  g.alpha = 1.f; g.bias = a.b3; g.residual = x; g.ldr = C; g.div_sqrt2 = 1;
-  launch_sgemm(g, s);
+  AttentionArgs aa{};
+  aa.x = x; aa.qs = ctx->op_stats; aa.gamma = a.gn_g; aa.beta = a.gn_b; aa.wqkv = a.wqkv; aa.bqkv = a.bqkv; aa.w3 = a.w3;
+  aa.b3 = a.b3; aa.out = out; aa.qstats = nullptr; aa.scratch = ctx->op_scratch; aa.B = B; aa.L = L; aa.C = C;
+  std::string e;
+  if (int rc = launch_attention(aa, s, &e)) { ctx->err = e; return rc; }
   CK(cudaGetLastError());
   return 0;
 }

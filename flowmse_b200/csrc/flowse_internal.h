@@ -220,6 +220,23 @@ void launch_sgemm(const SgemmArgs& a, cudaStream_t s);
 int sgemm_tile_rows(const SgemmArgs& a);           // M tile the launcher will pick (64 or 32)
 
 // ---------------------------------------------------------------------------------------------
+// Fused attention block (attention.cu): GroupNorm + QKV projection, then scores -> softmax -> PV -> NIN_3 -> residual
+// ---------------------------------------------------------------------------------------------
+struct AttentionArgs {
+  const float* x;            // [B][L][C] NHWC block input
+  const double* qs;          // quad statistics of x
+  const float* gamma; const float* beta;       // GroupNorm_0
+  const float* wqkv; const float* bqkv;        // [C][3C] (columns q | k | v), [3C]
+  const float* w3; const float* b3;            // NIN_3: [C][C] ([in, out]), [C]
+  float* out;                // [B][L][C]
+  double* qstats;            // optional quad statistics of out (zeroed buffer)
+  float* scratch;            // attention_scratch_floats(B, L) floats: q, kT, v
+  int B, L, C;
+};
+size_t attention_scratch_floats(int B, int L);
+int launch_attention(const AttentionArgs& a, cudaStream_t s, std::string* err);
+
+// ---------------------------------------------------------------------------------------------
 // Batched STFT / iSTFT + amplitude compression (stft.cu); n_fft 510, hop 128, hann, center=True
 // ---------------------------------------------------------------------------------------------
 size_t stft_basis_floats();                       // forward basis [510][512] + inverse basis [512][512] + window [512]
