@@ -41,6 +41,53 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// acc[r][0..3] += h[r] * w for the 8 rows of a CTA; h0 / h1 hold rows 0-3 / 4-7 of one shared-memory operand column
+__device__ __forceinline__ void fma_rows(float (&acc)[kR][4], const float4 h0, const float4 h1, const float4 w) {
+  const float h[kR] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    acc[r][0] = fmaf(h[r], w.x, acc[r][0]); acc[r][1] = fmaf(h[r], w.y, acc[r][1]);
+    acc[r][2] = fmaf(h[r], w.z, acc[r][2]); acc[r][3] = fmaf(h[r], w.w, acc[r][3]);
+  }
+}
+
+// The streaming loop all four GEMM phases share: acc[8][4] += sum_i colT[i0 + i*istep][0..7] (x) g[i0 + i*istep][0..3] for
+// i < n.  `g` rows are `gstride` floats apart in global memory (this thread's 4 contiguous floats), `colT` is the
+// [index][8 rows] shared-memory operand.  U rows are requested one batch ahead of the batch being consumed, so 2U 16-byte
+// loads per thread are in flight: with 256 threads that is 64 KB per SM, enough to cover the L2 latency at full rate
+// (the first version waited for every batch and ran 20x slower than its FMA count).
+template <int U>
+__device__ __forceinline__ void stream_fma(float (&acc)[kR][4], const float* __restrict__ g, size_t gstride,
+                                           const float* __restrict__ colT, int i0, int istep, int n, bool live) {
+  float4 cur[U], nxt[U];
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load = [&](float4 (&dst)[U], int base) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u;
+      dst[u] = (live && i < n) ? __ldg(reinterpret_cast<const float4*>(g + static_cast<size_t>(i0 + i * istep) * gstride)) : zero;
+    }
+  };
+  auto consume = [&](const float4 (&src)[U], int base) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u;
+      if (i < n) {
+        const float* col = colT + static_cast<size_t>(i0 + i * istep) * kR;
+        fma_rows(acc, *reinterpret_cast<const float4*>(col), *reinterpret_cast<const float4*>(col + 4), src[u]);
+      }
+    }
+  };
+  load(cur, 0);
+#pragma unroll 1
+  for (int base = 0; base < n; base += 2 * U) {
+    load(nxt, base + U);
+    consume(cur, base);
+    load(cur, base + 2 * U);
+    consume(nxt, base + U);
+  }
+}
+
 struct QkvK {
   const float* x;            // [B][L][C] NHWC block input
   const double* qs;          // quad statistics of x
@@ -53,10 +100,14 @@ struct QkvK {
   int L;
 };
 
-// grid (ceil(L / 8), B), 256 threads: thread n owns output columns n (q), C + n (k), 2C + n (v) for the CTA's 8 tokens.
-__global__ void __launch_bounds__(kThreads)
+constexpr int kQkvThreads = 384;      // 192 column quads of [q | k | v] x 2 halves of the input channels
+
+// grid (ceil(L / 8), B): thread (cq, half) owns output columns 4cq .. 4cq+3 of the 768 for the CTA's 8 tokens and sums the
+// input channels of its half; the two halves are folded through shared memory.
+__global__ void __launch_bounds__(kQkvThreads)
 attn_qkv_kernel(const QkvK k) {
   __shared__ __align__(16) float hT[kC][kR];        // normalised rows, transposed
+  __shared__ __align__(16) float red[192][kR][4];   // partial sums of the upper channel half
   __shared__ float s_mean[kGroups], s_rstd[kGroups];
   pdl_launch_dependents();
   pdl_wait();
@@ -66,10 +117,13 @@ attn_qkv_kernel(const QkvK k) {
   const int L = k.L;
   // the CTA's 8 x 256 input block, requested before the statistics are assembled (two dependent round trips overlap)
   float xr[kR];
+  float ga = 0.f, be = 0.f;
+  if (tid < kC) {
 #pragma unroll
-  for (int r = 0; r < kR; ++r)
-    xr[r] = (l0 + r < L) ? __ldg(k.x + (static_cast<size_t>(b) * L + l0 + r) * kC + tid) : 0.f;
-  const float ga = __ldg(k.gamma + tid), be = __ldg(k.beta + tid);
+    for (int r = 0; r < kR; ++r)
+      xr[r] = (l0 + r < L) ? __ldg(k.x + (static_cast<size_t>(b) * L + l0 + r) * kC + tid) : 0.f;
+    ga = __ldg(k.gamma + tid); be = __ldg(k.beta + tid);
+  }
   if (tid < kGroups) {                               // 32 groups of 8 channels = 2 quads
     double su = 0.0, sq = 0.0;
 #pragma unroll
@@ -87,7 +141,7 @@ attn_qkv_kernel(const QkvK k) {
     s_rstd[tid] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
   }
   __syncthreads();
-  {
+  if (tid < kC) {
     const int g = tid / (kC / kGroups);
     const float sc = s_rstd[g] * ga;
     const float sh = fmaf(-s_mean[g], sc, be);
@@ -95,47 +149,42 @@ attn_qkv_kernel(const QkvK k) {
     for (int r = 0; r < kR; ++r) hT[tid][r] = fmaf(xr[r], sc, sh);
   }
   __syncthreads();
-  float aq[kR], ak[kR], av[kR];
+  const int cq = tid % 192, half = tid / 192;
+  float acc[kR][4];
 #pragma unroll
-  for (int r = 0; r < kR; ++r) { aq[r] = 0.f; ak[r] = 0.f; av[r] = 0.f; }
-  const float* w = k.wqkv + tid;
-  constexpr int U = 4;                                // weight rows in flight per thread
-#pragma unroll 1
-  for (int c0 = 0; c0 < kC; c0 += U) {
-    float wq[U], wk[U], wv[U];
+  for (int r = 0; r < kR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+  stream_fma<8>(acc, k.wqkv + 4 * cq, 3 * kC, &hT[0][0], half * (kC / 2), 1, kC / 2, true);
+  if (half == 1) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float* row = w + static_cast<size_t>(c0 + u) * (3 * kC);
-      wq[u] = __ldg(row); wk[u] = __ldg(row + kC); wv[u] = __ldg(row + 2 * kC);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float4 h0 = *reinterpret_cast<const float4*>(&hT[c0 + u][0]);
-      const float4 h1 = *reinterpret_cast<const float4*>(&hT[c0 + u][4]);
-      const float h[kR] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-      for (int r = 0; r < kR; ++r) {
-        aq[r] = fmaf(h[r], wq[u], aq[r]); ak[r] = fmaf(h[r], wk[u], ak[r]); av[r] = fmaf(h[r], wv[u], av[r]);
-      }
-    }
+    for (int r = 0; r < kR; ++r) *reinterpret_cast<float4*>(&red[cq][r][0]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
   }
-  const float bq = __ldg(k.bqkv + tid), bk = __ldg(k.bqkv + kC + tid), bv = __ldg(k.bqkv + 2 * kC + tid);
+  __syncthreads();
+  if (half == 1) return;
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(k.bqkv) + cq);
 #pragma unroll
   for (int r = 0; r < kR; ++r) {
-    if (l0 + r < L) {
-      const size_t o = (static_cast<size_t>(b) * L + l0 + r) * kC + tid;
-      k.q[o] = aq[r] + bq;
-      k.v[o] = av[r] + bv;
-    }
+    const float4 o = *reinterpret_cast<const float4*>(&red[cq][r][0]);
+    acc[r][0] += o.x + bias.x; acc[r][1] += o.y + bias.y; acc[r][2] += o.z + bias.z; acc[r][3] += o.w + bias.w;
   }
-  // keys transposed: kT[b][n][l0 .. l0+7] (32 contiguous bytes per thread)
-  float* kt = k.kT + (static_cast<size_t>(b) * kC + tid) * L + l0;
-  if (l0 + kR <= L && (L & 3) == 0) {
-    *reinterpret_cast<float4*>(kt) = make_float4(ak[0] + bk, ak[1] + bk, ak[2] + bk, ak[3] + bk);
-    *reinterpret_cast<float4*>(kt + 4) = make_float4(ak[4] + bk, ak[5] + bk, ak[6] + bk, ak[7] + bk);
-  } else {
+  const int which = (4 * cq) / kC, n0 = (4 * cq) % kC;     // 0 q, 1 k, 2 v
+  if (which != 1) {
+    float* dst = (which == 0 ? k.q : k.v) + (static_cast<size_t>(b) * L + l0) * kC + n0;
 #pragma unroll
-    for (int r = 0; r < kR; ++r) if (l0 + r < L) kt[r] = ak[r] + bk;
+    for (int r = 0; r < kR; ++r)
+      if (l0 + r < L) *reinterpret_cast<float4*>(dst + static_cast<size_t>(r) * kC) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  } else {
+    // keys transposed: kT[b][n][l0 .. l0+7]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float* kt = k.kT + (static_cast<size_t>(b) * kC + n0 + i) * L + l0;
+      if (l0 + kR <= L) {
+        *reinterpret_cast<float4*>(kt) = make_float4(acc[0][i], acc[1][i], acc[2][i], acc[3][i]);
+        *reinterpret_cast<float4*>(kt + 4) = make_float4(acc[4][i], acc[5][i], acc[6][i], acc[7][i]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kR; ++r) if (l0 + r < L) kt[r] = acc[r][i];
+      }
+    }
   }
 }
 
@@ -146,18 +195,21 @@ struct CoreK {
   const float* b3;           // [C]
   float* out;                // [B][L][C]
   double* qstats;            // optional quad statistics of out (zeroed buffer)
-  int L, Lpad;               // Lpad: L rounded up to a multiple of 2 * kThreads (keys per scores pass)
+  int L, Lpad;               // Lpad: L rounded up to a multiple of 512 (keys per scores pass)
   float scale;               // C^-1/2
 };
 
+constexpr int kKeysPerPass = 512;      // 128 key quads x 2 channel halves = 256 threads
+
 // grid (ceil(L / 8), B), 256 threads.  Dynamic shared memory: S [8][Lpad] scores, Pt [Lpad][8] probabilities (transposed),
-// qT / oT [C][8] query rows, later the context rows.
+// qT / oT [C][8] query rows, later the context rows, red [4][8][C] partial sums of the thread groups.
 __global__ void __launch_bounds__(kThreads)
 attn_core_kernel(const CoreK k) {
   extern __shared__ __align__(16) float sm[];
   float* S = sm;                                     // [kR][Lpad]
   float* Pt = S + static_cast<size_t>(kR) * k.Lpad;  // [Lpad][kR]
   float* qT = Pt + static_cast<size_t>(k.Lpad) * kR; // [kC][kR]
+  float* red = qT + kC * kR;                         // [4][kR][kC]
   pdl_launch_dependents();
   pdl_wait();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -169,34 +221,35 @@ attn_core_kernel(const CoreK k) {
   for (int r = 0; r < kR; ++r)
     qT[tid * kR + r] = (l0 + r < L) ? __ldg(k.q + (static_cast<size_t>(b) * L + l0 + r) * kC + tid) : 0.f;
   __syncthreads();
-  // ---- scores: thread owns keys (2 tid, 2 tid + 1) of each 512-key pass, all 8 rows
-  const float* kTb = k.kT + static_cast<size_t>(b) * kC * L;
-  for (int key0 = 0; key0 < L; key0 += 2 * kThreads) {
-    const int key = key0 + 2 * tid;
-    const bool inb = key < L;                        // L is even (a multiple of 4): key + 1 < L as well
-    float a0[kR], a1[kR];
+  // ---- scores: thread (kq, half) owns keys 4kq .. 4kq+3 of each 512-key pass for all 8 rows and sums its half of the
+  //      channels; kT[c][key] is contiguous in the keys
+  {
+    const int kq = tid & 127, half = tid >> 7;
+    const float* kTb = k.kT + static_cast<size_t>(b) * kC * L;
+    for (int key0 = 0; key0 < L; key0 += kKeysPerPass) {
+      const int key = key0 + 4 * kq;
+      const bool live = key < L;                     // L is a multiple of 4: the whole quad is inside or outside
+      float acc[kR][4];
 #pragma unroll
-    for (int r = 0; r < kR; ++r) { a0[r] = 0.f; a1[r] = 0.f; }
-    constexpr int U = 8;                             // key rows (channels) in flight per thread
-#pragma unroll 1
-    for (int c0 = 0; c0 < kC; c0 += U) {
-      float2 kv[U];
+      for (int r = 0; r < kR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+      stream_fma<8>(acc, kTb + key, L, qT, half * (kC / 2), 1, kC / 2, live);
+      if (half == 1) {
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        kv[u] = inb ? __ldg(reinterpret_cast<const float2*>(kTb + static_cast<size_t>(c0 + u) * L + key)) : make_float2(0.f, 0.f);
+        for (int r = 0; r < kR; ++r)
+          *reinterpret_cast<float4*>(S + static_cast<size_t>(r) * k.Lpad + key) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      }
+      __syncthreads();
+      if (half == 0) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const float4 q0 = *reinterpret_cast<const float4*>(qT + (c0 + u) * kR);
-        const float4 q1 = *reinterpret_cast<const float4*>(qT + (c0 + u) * kR + 4);
-        const float qq[kR] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-        for (int r = 0; r < kR; ++r) { a0[r] = fmaf(qq[r], kv[u].x, a0[r]); a1[r] = fmaf(qq[r], kv[u].y, a1[r]); }
+        for (int r = 0; r < kR; ++r) {
+          float4* dst = reinterpret_cast<float4*>(S + static_cast<size_t>(r) * k.Lpad + key);
+          const float4 o = *dst;
+          *dst = live ? make_float4((acc[r][0] + o.x) * k.scale, (acc[r][1] + o.y) * k.scale, (acc[r][2] + o.z) * k.scale,
+                                    (acc[r][3] + o.w) * k.scale)
+                      : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
       }
     }
-#pragma unroll
-    for (int r = 0; r < kR; ++r)
-      *reinterpret_cast<float2*>(S + static_cast<size_t>(r) * k.Lpad + key) =
-          inb ? make_float2(a0[r] * k.scale, a1[r] * k.scale) : make_float2(-INFINITY, -INFINITY);
   }
   __syncthreads();
   // ---- softmax over the keys: warp r owns row r (layerspp.py:84)
@@ -211,68 +264,46 @@ attn_core_kernel(const CoreK k) {
     for (int i = lane; i < L; i += 32) Pt[static_cast<size_t>(i) * kR + warp] = __fdiv_rn(expf(row[i] - m), sum);
   }
   __syncthreads();
-  // ---- context rows h = P v: thread owns channel tid for all 8 rows; v[l][tid] is coalesced
-  float o[kR];
-#pragma unroll
-  for (int r = 0; r < kR; ++r) o[r] = 0.f;
+  // ---- context rows h = P v: thread (cq, kg) owns channels 4cq .. 4cq+3 and every 4th key starting at kg
+  const int cq = tid & 63, grp = tid >> 6;
   {
-    const float* vb = k.v + static_cast<size_t>(b) * L * kC + tid;
-    constexpr int U = 8;
-    int l = 0;
-#pragma unroll 1
-    for (; l + U <= L; l += U) {
-      float vv[U];
+    float acc[kR][4];
 #pragma unroll
-      for (int u = 0; u < U; ++u) vv[u] = __ldg(vb + static_cast<size_t>(l + u) * kC);
+    for (int r = 0; r < kR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+    const int nkeys = (L - grp + 3) / 4;             // keys grp, grp + 4, ... < L
+    stream_fma<8>(acc, k.v + static_cast<size_t>(b) * L * kC + 4 * cq, kC, Pt, grp, 4, nkeys, true);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const float4 p0 = *reinterpret_cast<const float4*>(Pt + static_cast<size_t>(l + u) * kR);
-        const float4 p1 = *reinterpret_cast<const float4*>(Pt + static_cast<size_t>(l + u) * kR + 4);
-        const float pp[kR] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-#pragma unroll
-        for (int r = 0; r < kR; ++r) o[r] = fmaf(pp[r], vv[u], o[r]);
-      }
-    }
-    for (; l < L; ++l) {
-      const float vv = __ldg(vb + static_cast<size_t>(l) * kC);
-#pragma unroll
-      for (int r = 0; r < kR; ++r) o[r] = fmaf(Pt[static_cast<size_t>(l) * kR + r], vv, o[r]);
-    }
+    for (int r = 0; r < kR; ++r)
+      *reinterpret_cast<float4*>(red + (static_cast<size_t>(grp) * kR + r) * kC + 4 * cq) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
   }
-  // park the context rows transposed (the query rows are no longer needed)
+  __syncthreads();
+  // fold the 4 key groups (fixed order) and park the context rows transposed (the query rows are no longer needed)
   float* oT = qT;
 #pragma unroll
-  for (int r = 0; r < kR; ++r) oT[tid * kR + r] = o[r];
+  for (int r = 0; r < kR; ++r)
+    oT[tid * kR + r] = (red[(0 * kR + r) * kC + tid] + red[(1 * kR + r) * kC + tid]) + (red[(2 * kR + r) * kC + tid] + red[(3 * kR + r) * kC + tid]);
   __syncthreads();
-  // ---- NIN_3 + residual + 1/sqrt(2): thread owns output channel tid
-  float y[kR];
-#pragma unroll
-  for (int r = 0; r < kR; ++r) y[r] = 0.f;
+  // ---- NIN_3: thread (nq, cg) owns output channels 4nq .. 4nq+3 and input channels 64cg .. 64cg+63
   {
-    const float* w = k.w3 + tid;
-    constexpr int U = 8;
-#pragma unroll 1
-    for (int c0 = 0; c0 < kC; c0 += U) {
-      float wv[U];
+    float acc[kR][4];
 #pragma unroll
-      for (int u = 0; u < U; ++u) wv[u] = __ldg(w + static_cast<size_t>(c0 + u) * kC);
+    for (int r = 0; r < kR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+    stream_fma<8>(acc, k.w3 + 4 * cq, kC, oT, grp * (kC / 4), 1, kC / 4, true);
+    __syncthreads();                                 // everyone has read its share of red
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const float4 h0 = *reinterpret_cast<const float4*>(oT + (c0 + u) * kR);
-        const float4 h1 = *reinterpret_cast<const float4*>(oT + (c0 + u) * kR + 4);
-        const float h[kR] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-        for (int r = 0; r < kR; ++r) y[r] = fmaf(h[r], wv[u], y[r]);
-      }
-    }
+    for (int r = 0; r < kR; ++r)
+      *reinterpret_cast<float4*>(red + (static_cast<size_t>(grp) * kR + r) * kC + 4 * cq) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
   }
+  __syncthreads();
+  // ---- residual + 1/sqrt(2) + statistics: thread owns output channel tid
   const float bias = __ldg(k.b3 + tid);
   float qs_s = 0.f, qs_q = 0.f;
 #pragma unroll
   for (int r = 0; r < kR; ++r) {
     if (l0 + r < L) {
+      const float y = (red[(0 * kR + r) * kC + tid] + red[(1 * kR + r) * kC + tid]) + (red[(2 * kR + r) * kC + tid] + red[(3 * kR + r) * kC + tid]);
       const size_t oidx = (static_cast<size_t>(b) * L + l0 + r) * kC + tid;
-      const float val = __fdiv_rn(__ldg(k.x + oidx) + (y[r] + bias), kSqrt2);
+      const float val = __fdiv_rn(__ldg(k.x + oidx) + (y + bias), kSqrt2);
       k.out[oidx] = val;
       qs_s += val; qs_q += val * val;
     }
@@ -295,9 +326,9 @@ size_t attention_scratch_floats(int B, int L) { return static_cast<size_t>(3) * 
 
 int launch_attention(const AttentionArgs& a, cudaStream_t s, std::string* err) {
   if (a.C != kC) { if (err) *err = "attention: the kernels are specialised to 256 channels"; return 1; }
-  if (a.L <= 0 || (a.L & 1)) { if (err) *err = "attention: token count must be a positive even number"; return 1; }
-  const int Lpad = ((a.L + 2 * kThreads - 1) / (2 * kThreads)) * (2 * kThreads);
-  const size_t smem = (static_cast<size_t>(2) * kR * Lpad + static_cast<size_t>(kC) * kR) * sizeof(float);
+  if (a.L <= 0 || (a.L & 3)) { if (err) *err = "attention: token count must be a positive multiple of 4"; return 1; }
+  const int Lpad = ((a.L + kKeysPerPass - 1) / kKeysPerPass) * kKeysPerPass;
+  const size_t smem = (static_cast<size_t>(2) * kR * Lpad + static_cast<size_t>(kC) * kR + static_cast<size_t>(4) * kR * kC) * sizeof(float);
   if (smem > 200 * 1024) { if (err) *err = "attention: too many tokens for the shared-memory score rows"; return 1; }
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
@@ -310,7 +341,7 @@ int launch_attention(const AttentionArgs& a, cudaStream_t s, std::string* err) {
   float* v = kT + static_cast<size_t>(a.B) * a.L * kC;
   dim3 grid((a.L + kR - 1) / kR, a.B);
   QkvK qk{a.x, a.qs, a.gamma, a.beta, a.wqkv, a.bqkv, q, kT, v, a.L};
-  launch_k(attn_qkv_kernel, grid, dim3(kThreads), 0, s, qk);
+  launch_k(attn_qkv_kernel, grid, dim3(kQkvThreads), 0, s, qk);
   CoreK ck{a.x, q, kT, v, a.w3, a.b3, a.out, a.qstats, a.L, Lpad, 1.0f / sqrtf(static_cast<float>(kC))};
   launch_k(attn_core_kernel, grid, dim3(kThreads), smem, s, ck);
   return 0;

@@ -105,7 +105,6 @@ struct HaloParams {
   int div_sqrt2;
   double* qstats;
   long long* dbg;   // optional per-CTA wait-cycle counters (FLOWSE_CONV_DBG=1): 8 per CTA
-  int layout;       // warp-role layout: 0 = producer / MMA issuer first (warps 0, 1), 1 = MMA issuer in the LAST warp
 };
 
 // fused operand sources (XF variant), device view of FusedOperand
@@ -197,7 +196,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ uint32_t tmem_slot_var;
   __shared__ float s_qs[2][kEpiWarps][C::COLS_PER_WARP / 4 > 0 ? C::COLS_PER_WARP / 4 : 1][2];
   __shared__ __align__(16) float s_xsc[XF ? kXfMaxC : 4], s_xsh[XF ? kXfMaxC : 4];   // GroupNorm scale / shift per channel
-  __shared__ float s_xmean[kGroups], s_xrstd[kGroups];
 
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = ptx::smem_u32(bars);
@@ -215,16 +213,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // Warp roles.  The SM's issue arbiter favours the warp with the HIGHEST index among the eligible ones, so layout 1 puts
-  // the single MMA-issuing thread (one instruction per ~20 cycles that must not wait behind ALU-heavy warps) last and the
-  // transform / epilogue warps first; layout 0 is the original order.  Epilogue base is a multiple of 4 (TMEM quadrants).
-  constexpr int kWarps = (XF ? NUM_THREADS_XF : NUM_THREADS) / 32;
-  const int w_xf0 = p.layout ? 0 : kFirstXfWarp;
-  const int w_epi0 = p.layout ? (XF ? kXfWarps : 0) : kFirstEpiWarp;
-  const int w_alloc = p.layout ? kWarps - 4 : 2;
-  const int w_tma = p.layout ? kWarps - 3 : 0;
-  const int w_mma = p.layout ? kWarps - 1 : 1;
-  const bool is_xf = XF && warp >= w_xf0 && warp < w_xf0 + kXfWarps;
+  // Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 epilogue, 12..19 operand transform (XF).  (Putting
+  // the MMA-issuing warp last - the issue arbiter favours high warp indices - was measured and makes no difference.)
+  constexpr int w_tma = 0, w_mma = 1, w_alloc = 2, w_epi0 = kFirstEpiWarp, w_xf0 = kFirstXfWarp;
+  const bool is_xf = XF && warp >= w_xf0;
   const bool is_epi = warp >= w_epi0 && warp < w_epi0 + kEpiWarps;
   const int nchunks = p.nchunk_main + p.nchunk_sc;
   const int rank = PAIR ? static_cast<int>(ptx::cluster_ctarank()) : 0;
@@ -394,129 +386,164 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         p.dbg[blockIdx.x * 8 + 2] = w_a; p.dbg[blockIdx.x * 8 + 3] = w_b;
       }
     }
+  } else if (XF && warp == 3) {
+    // ------------------------------------------------------------------ GroupNorm table builder (XF only)
+    // Per-channel scale / shift (rstd*gamma, beta - mean*rstd*gamma) of the main operand for every batch element this CTA
+    // meets, same arithmetic as the standalone prep (kernels_gn.cu: fp64 group sums -> fp32 mean / rstd).  A warp of its
+    // own: the fp64 divide / sqrt are subroutine calls, which would force the transform warps to spill the activations they
+    // hold in flight, and the table is ready while their first loads are still on the way.
+    if (xf.a.s1 != nullptr && xf.gamma != nullptr) {
+      const int Ca = xf.a.C1 + xf.a.C2;
+      const int cpg = Ca / kGroups;
+      int cur_b = -1;
+      for (int item = item0; item < p.num_items; item += item_stride) {
+        const int b = decode_tile<BN, PAIR>(p, item, rank).b;
+        if (b == cur_b) continue;
+        cur_b = b;
+        double su = 0.0, sq = 0.0;                      // lane = group
+        {
+          const int qpg = cpg >> 2, q1 = xf.a.C1 >> 2;
+          for (int jj = 0; jj < qpg; ++jj) {
+            const int qd = lane * qpg + jj;
+#pragma unroll
+            for (int r = 0; r < kStatReplicas; ++r) {
+              const double2 v = (qd < q1)
+                  ? reinterpret_cast<const double2*>(qstat_slot(xf.qs1, b, r, q1))[qd]
+                  : reinterpret_cast<const double2*>(qstat_slot(xf.qs2, b, r, xf.a.C2 >> 2))[qd - q1];
+              su += v.x; sq += v.y;
+            }
+          }
+        }
+        const double n = static_cast<double>(p.H) * p.W * cpg;
+        const double mean_d = su / n;
+        double var = sq / n - mean_d * mean_d;
+        if (var < 0.0) var = 0.0;
+        const float mean = static_cast<float>(mean_d);
+        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
+        named_bar_sync(2, kXfWarps * 32 + 32);          // the transform warps no longer read the previous table
+        for (int c = lane; c < Ca; c += 32) {
+          const int g = c / cpg;
+          const float m = __shfl_sync(0xffffffffu, mean, g), rs = __shfl_sync(0xffffffffu, rstd, g);
+          const float sc = rs * __ldg(xf.gamma + c);
+          s_xsc[c] = sc;
+          s_xsh[c] = fmaf(-m, sc, __ldg(xf.beta + c));
+        }
+        named_bar_sync(3, kXfWarps * 32 + 32);          // table complete (bar.sync orders the shared-memory writes)
+      }
+    }
   } else if (is_xf) {
-    // ------------------------------------------------------------------ operand transform (8 warps, XF only)
+    // ------------------------------------------------------------------ operand transform (warps 12..19, XF only)
+    // Work unit = "batch": up to 4 operand rows of one 64-channel chunk per thread.  A 3x3 chunk (180 halo rows) is two
+    // batches of 3 rows, a 1x1 shortcut chunk (128 centre rows) one batch of 4.  The global loads of batch q+1 are issued
+    // as soon as batch q has been consumed, BEFORE the wait for the next free operand stage: in steady state the
+    // transform runs ahead of the tensor core, so the L2 / HBM latency hides behind that wait - in particular for the
+    // shortcut chunks, which the tensor core consumes in ~900 cycles each.
     const int xt = static_cast<int>(threadIdx.x) - w_xf0 * 32;            // 0..255
     const int j = xt & 7;                      // 16-byte column of the 128-byte operand row: channels 8j .. 8j+7 of the chunk
     const int r0 = xt >> 3;                    // rows r0 + 32 i
+    const int Ca = xf.a.C1 + xf.a.C2;
+    const bool norm_a = xf.a.s1 != nullptr && xf.gamma != nullptr;
+    const int nb_item = 2 * p.nchunk_main + p.nchunk_sc;                 // batches per work item
+    const int n_my_items = (p.num_items - item0 + item_stride - 1) / item_stride;
+    const int Q = n_my_items > 0 ? n_my_items * nb_item : 0;
+    float4 v0[4], v1[4];                       // the batch in flight: 4 rows x 8 channels of this thread
+    // batch q -> (tile, chunk, half); row slot i -> halo row, validity
+    auto batch_of = [&](int q, TileCoord& t, int& c, int& half) {
+      const int it = q / nb_item, w = q - it * nb_item;
+      t = decode_tile<BN, PAIR>(p, item0 + it * item_stride, rank);
+      if (w < 2 * p.nchunk_main) { c = w >> 1; half = w & 1; } else { c = p.nchunk_main + (w - 2 * p.nchunk_main); half = 0; }
+    };
+    auto row_of = [&](bool main, int half, int i, int& r, bool& valid) {
+      if (main) { r = r0 + 32 * (3 * half + i); valid = i < 3 && r < A_ROWS; }
+      else { const int idx = r0 + 32 * i; r = ((idx >> 3) + 1) * HALO_W + (idx & 7) + 1; valid = true; }
+    };
+    auto issue = [&](int q) {
+      TileCoord t; int c, half;
+      batch_of(q, t, c, half);
+      const bool main = c < p.nchunk_main;
+      const XfOperand& src = main ? xf.a : xf.x;
+      if (src.s1 == nullptr) return;
+      const int cg = (main ? c : c - p.nchunk_main) * BK;
+      const float* base; int ld;
+      if (cg < src.C1) { base = src.s1 + cg; ld = src.C1; } else { base = src.s2 + (cg - src.C1); ld = src.C2; }
+      base += static_cast<size_t>(t.b) * p.H * p.W * ld + j * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int r; bool valid;
+        row_of(main, half, i, r, valid);
+        const int hy = r / HALO_W, hx = r - hy * HALO_W;
+        const int h = t.h0 - 1 + hy, w = t.w0 - 1 + hx;
+        v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i];
+        if (valid && h >= 0 && h < p.H && w >= 0 && w < p.W) {
+          const float4* g = reinterpret_cast<const float4*>(base + (static_cast<size_t>(h) * p.W + w) * ld);
+          v0[i] = __ldg(g); v1[i] = __ldg(g + 1);
+        }
+      }
+    };
     int as = 0;
     uint32_t aph = 0;
     int cur_b = -1;
     float vmax = 0.f;
-    const int Ca = xf.a.C1 + xf.a.C2;
-    for (int item = item0; item < p.num_items; item += item_stride) {
-      const TileCoord t = decode_tile<BN, PAIR>(p, item, rank);
-      if (xf.a.s1 != nullptr && xf.gamma != nullptr && t.b != cur_b) {
-        // per-channel scale / shift of this batch element, same arithmetic as the standalone prep (kernels_gn.cu)
-        named_bar_sync(2, kXfWarps * 32);        // nobody still reads the previous table
-        if (xt < kGroups) {
-          const int qpg = (Ca / kGroups) >> 2, q1 = xf.a.C1 >> 2;
-          double su = 0.0, sq = 0.0;
-          for (int jj = 0; jj < qpg; ++jj) {
-            const int qd = xt * qpg + jj;
-#pragma unroll
-            for (int r = 0; r < kStatReplicas; ++r) {
-              const double2 v = (qd < q1)
-                  ? reinterpret_cast<const double2*>(qstat_slot(xf.qs1, t.b, r, q1))[qd]
-                  : reinterpret_cast<const double2*>(qstat_slot(xf.qs2, t.b, r, xf.a.C2 >> 2))[qd - q1];
-              su += v.x; sq += v.y;
-            }
-          }
-          const double n = static_cast<double>(p.H) * p.W * (Ca / kGroups);
-          const double mean = su / n;
-          double var = sq / n - mean * mean;
-          if (var < 0.0) var = 0.0;
-          s_xmean[xt] = static_cast<float>(mean);
-          s_xrstd[xt] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
+    auto process = [&](int q) {
+      TileCoord t; int c, half;
+      batch_of(q, t, c, half);
+      const bool main = c < p.nchunk_main;
+      const XfOperand& src = main ? xf.a : xf.x;
+      const bool first = half == 0, last = !main || half == 1;
+      if (first) {
+        if (norm_a && c == 0 && t.b != cur_b) {
+          // the scale / shift table of this batch element is built by warp 3 (below): release the old one, wait for the new
+          named_bar_sync(2, kXfWarps * 32 + 32);
+          named_bar_sync(3, kXfWarps * 32 + 32);
+          cur_b = t.b;
         }
-        named_bar_sync(2, kXfWarps * 32);
-        const int cpg = Ca / kGroups;
-        for (int c = xt; c < Ca; c += kXfWarps * 32) {
-          const int g = c / cpg;
-          const float sc = s_xrstd[g] * __ldg(xf.gamma + c);
-          s_xsc[c] = sc;
-          s_xsh[c] = fmaf(-s_xmean[g], sc, __ldg(xf.beta + c));
-        }
-        named_bar_sync(2, kXfWarps * 32);
-        cur_b = t.b;
-      }
-      for (int c = 0; c < nchunks; ++c) {
-        const bool main = c < p.nchunk_main;
-        const XfOperand& src = main ? xf.a : xf.x;
         ptx::mbar_wait(a_empty(as), aph ^ 1u);
-        if (src.s1 != nullptr) {
-          const int cg = (main ? c : c - p.nchunk_main) * BK;             // first channel of the chunk in the concat
-          const float* base; int ld;
-          if (cg < src.C1) { base = src.s1 + cg; ld = src.C1; } else { base = src.s2 + (cg - src.C1); ld = src.C2; }
-          base += static_cast<size_t>(t.b) * p.H * p.W * ld + j * 8;
-          const bool norm = main && xf.gamma != nullptr;
-          float4 sc0, sc1, sh0, sh1;
-          if (norm) {
-            sc0 = *reinterpret_cast<const float4*>(s_xsc + cg + j * 8); sc1 = *reinterpret_cast<const float4*>(s_xsc + cg + j * 8 + 4);
-            sh0 = *reinterpret_cast<const float4*>(s_xsh + cg + j * 8); sh1 = *reinterpret_cast<const float4*>(s_xsh + cg + j * 8 + 4);
-          }
-          const uint32_t stage = sA(as);
-          auto emit = [&](int r, bool inb, float4 a0, float4 a1) {
-            uint2 h0 = make_uint2(0u, 0u), l0 = h0, h1 = h0, l1 = h0;
-            if (inb) {
-              if (norm) { a0 = norm_act(a0, sc0, sh0, xf.silu); a1 = norm_act(a1, sc1, sh1, xf.silu); }
-              split4(a0, h0, l0); split4(a1, h1, l1);
-              vmax = amax4(a0, amax4(a1, vmax));
-            }
-            const uint32_t dst = stage + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
-            ptx::st_shared_v4(dst, pack8(h0, h1));
-            ptx::st_shared_v4(dst + A_PLANE_STRIDE, pack8(l0, l1));
-          };
-          if (main) {
-            // all 180 halo rows; loads of 3 rows in flight per thread
-#pragma unroll
-            for (int i0 = 0; i0 < 6; i0 += 3) {
-              float4 v0[3], v1[3]; bool inb[3]; int rr[3];
-#pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                const int r = r0 + 32 * (i0 + i);
-                rr[i] = r;
-                const int hy = r / HALO_W, hx = r - hy * HALO_W;
-                const int h = t.h0 - 1 + hy, w = t.w0 - 1 + hx;
-                inb[i] = r < A_ROWS && h >= 0 && h < p.H && w >= 0 && w < p.W;
-                v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i];
-                if (inb[i]) {
-                  const float4* g = reinterpret_cast<const float4*>(base + (static_cast<size_t>(h) * p.W + w) * ld);
-                  v0[i] = __ldg(g); v1[i] = __ldg(g + 1);
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < 3; ++i) if (rr[i] < A_ROWS) emit(rr[i], inb[i], v0[i], v1[i]);
-            }
-          } else {
-            // 1x1 shortcut: the 128 centre rows only (always inside the image)
-            float4 v0[4], v1[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int idx = r0 + 32 * i;
-              const int h = t.h0 + (idx >> 3), w = t.w0 + (idx & 7);
-              const float4* g = reinterpret_cast<const float4*>(base + (static_cast<size_t>(h) * p.W + w) * ld);
-              v0[i] = __ldg(g); v1[i] = __ldg(g + 1);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int idx = r0 + 32 * i;
-              emit(((idx >> 3) + 1) * HALO_W + (idx & 7) + 1, true, v0[i], v1[i]);
-            }
-          }
-          ptx::fence_proxy_async();            // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      }
+      if (src.s1 != nullptr) {
+        const uint32_t stage = sA(as);
+        float4 sc0, sc1, sh0, sh1;
+        sc0 = sc1 = sh0 = sh1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (main && norm_a) {
+          const int cg = c * BK + j * 8;
+          sc0 = *reinterpret_cast<const float4*>(s_xsc + cg); sc1 = *reinterpret_cast<const float4*>(s_xsc + cg + 4);
+          sh0 = *reinterpret_cast<const float4*>(s_xsh + cg); sh1 = *reinterpret_cast<const float4*>(s_xsh + cg + 4);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int r; bool valid;
+          row_of(main, half, i, r, valid);
+          if (!valid) continue;
+          const int hy = r / HALO_W, hx = r - hy * HALO_W;
+          const int h = t.h0 - 1 + hy, w = t.w0 - 1 + hx;
+          uint2 h0 = make_uint2(0u, 0u), l0 = h0, h1 = h0, l1 = h0;
+          if (h >= 0 && h < p.H && w >= 0 && w < p.W) {          // zero padding of the ACTIVATED tensor outside the image
+            float4 a0 = v0[i], a1 = v1[i];
+            if (main && norm_a) { a0 = norm_act(a0, sc0, sh0, xf.silu); a1 = norm_act(a1, sc1, sh1, xf.silu); }
+            split4(a0, h0, l0); split4(a1, h1, l1);
+            vmax = amax4(a0, amax4(a1, vmax));
+          }
+          const uint32_t dst = stage + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
+          ptx::st_shared_v4(dst, pack8(h0, h1));
+          ptx::st_shared_v4(dst + A_PLANE_STRIDE, pack8(l0, l1));
+        }
+      }
+      if (q + 1 < Q) issue(q + 1);           // v0 / v1 are free again: next batch's loads fly during the fence / arrive / wait
+      if (last) {
+        if (src.s1 != nullptr) ptx::fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(a_full(as));
         if (++as == A_STAGES) { as = 0; aph ^= 1u; }
       }
-    }
+    };
+    if (Q > 0) issue(0);
+#pragma unroll 1
+    for (int q = 0; q < Q; ++q) process(q);
     if (vmax > kHalfMax && xf.overflow) atomicAdd(xf.overflow, 1ull);
   } else if (is_epi) {
     // ------------------------------------------------------------------ epilogue (8 warps)
     // Two warps per TMEM lane quadrant, each owning half of the tile's columns, CH columns per pass: TMEM -> registers
     // (slots summed in IEEE fp32) -> padded smem staging tile -> row-contiguous float4 residual loads / output stores.
-    const int e = warp - w_epi0;
+    const int e = warp - kFirstEpiWarp;
     const int q = warp & 3;
     const int half = e >> 2;
     constexpr int CH = C::CH;
@@ -532,7 +559,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int cj = (lane % LPR) * 4;
     const int col_base = half * C::COLS_PER_WARP;
     const float post = p.div_sqrt2 ? 0.70710678118654752440f : 1.0f;
-    const int etid = static_cast<int>(threadIdx.x) - w_epi0 * 32;
+    const int etid = static_cast<int>(threadIdx.x) - kFirstEpiWarp * 32;
     int it = 0;
     for (int item = item0; item < p.num_items; item += item_stride, ++it) {
       const TileCoord t = decode_tile<BN, PAIR>(p, item, rank);
@@ -727,8 +754,6 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   p.Cout = a.Cout; p.ldc = a.ldc; p.wscale_inv = a.wscale_inv;
   p.bias = a.bias; p.bias_bstride = a.bias_bstride; p.residual = a.residual; p.out = a.out;
   p.div_sqrt2 = a.div_sqrt2; p.qstats = a.qstats;
-  static const int layout = [] { const char* e = getenv("FLOWSE_HALO_LAYOUT"); return e ? atoi(e) : 0; }();
-  p.layout = layout;
   const bool has_x = a.X != nullptr || a.fX.s1 != nullptr;
   p.nchunk_sc = has_x ? a.Cin2 / BK : 0;
   const int K = 9 * a.Cin + (has_x ? a.Cin2 : 0);
