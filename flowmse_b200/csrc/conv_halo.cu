@@ -441,7 +441,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int xt = static_cast<int>(threadIdx.x) - w_xf0 * 32;            // 0..255
     const int j = xt & 7;                      // 16-byte column of the 128-byte operand row: channels 8j .. 8j+7 of the chunk
     const int r0 = xt >> 3;                    // rows r0 + 32 i
-    const int Ca = xf.a.C1 + xf.a.C2;
     const bool norm_a = xf.a.s1 != nullptr && xf.gamma != nullptr;
     const int nb_item = 2 * p.nchunk_main + p.nchunk_sc;                 // batches per work item
     const int n_my_items = (p.num_items - item0 + item_stride - 1) / item_stride;
