@@ -400,6 +400,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int b = decode_tile<BN, PAIR>(p, item, rank).b;
         if (b == cur_b) continue;
         cur_b = b;
+        float ga[kXfMaxC / 32], be[kXfMaxC / 32];       // requested before the statistics: one global round trip in all
+#pragma unroll
+        for (int i = 0; i < kXfMaxC / 32; ++i) {
+          const int c = lane + 32 * i;
+          ga[i] = c < Ca ? __ldg(xf.gamma + c) : 0.f; be[i] = c < Ca ? __ldg(xf.beta + c) : 0.f;
+        }
         double su = 0.0, sq = 0.0;                      // lane = group
         {
           const int qpg = cpg >> 2, q1 = xf.a.C1 >> 2;
@@ -421,44 +427,47 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const float mean = static_cast<float>(mean_d);
         const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
         named_bar_sync(2, kXfWarps * 32 + 32);          // the transform warps no longer read the previous table
-        for (int c = lane; c < Ca; c += 32) {
-          const int g = c / cpg;
+#pragma unroll
+        for (int i = 0; i < kXfMaxC / 32; ++i) {
+          const int c = lane + 32 * i;
+          const int g = (c < Ca ? c : 0) / cpg;
           const float m = __shfl_sync(0xffffffffu, mean, g), rs = __shfl_sync(0xffffffffu, rstd, g);
-          const float sc = rs * __ldg(xf.gamma + c);
-          s_xsc[c] = sc;
-          s_xsh[c] = fmaf(-m, sc, __ldg(xf.beta + c));
+          if (c < Ca) {
+            const float sc = rs * ga[i];
+            s_xsc[c] = sc;
+            s_xsh[c] = fmaf(-m, sc, be[i]);
+          }
         }
         named_bar_sync(3, kXfWarps * 32 + 32);          // table complete (bar.sync orders the shared-memory writes)
       }
     }
   } else if (is_xf) {
     // ------------------------------------------------------------------ operand transform (warps 12..19, XF only)
-    // Work unit = "batch": up to 4 operand rows of one 64-channel chunk per thread.  A 3x3 chunk (180 halo rows) is two
-    // batches of 3 rows, a 1x1 shortcut chunk (128 centre rows) one batch of 4.  The global loads of batch q+1 are issued
-    // as soon as batch q has been consumed, BEFORE the wait for the next free operand stage: in steady state the
-    // transform runs ahead of the tensor core, so the L2 / HBM latency hides behind that wait - in particular for the
-    // shortcut chunks, which the tensor core consumes in ~900 cycles each.
+    // Work unit = one 64-channel chunk: 6 operand rows per thread for a 3x3 chunk (180 halo rows), 4 for a 1x1 shortcut
+    // chunk (128 centre rows).  ALL global loads of chunk c+1 (48 KB per SM) are issued as soon as chunk c has been
+    // consumed, before the wait for the next free operand stage: the transform runs ahead of the tensor core, so the
+    // HBM latency under load (several microseconds) hides behind that wait, like the TMA prefetch of the halo it replaces.
     const int xt = static_cast<int>(threadIdx.x) - w_xf0 * 32;            // 0..255
     const int j = xt & 7;                      // 16-byte column of the 128-byte operand row: channels 8j .. 8j+7 of the chunk
     const int r0 = xt >> 3;                    // rows r0 + 32 i
     const bool norm_a = xf.a.s1 != nullptr && xf.gamma != nullptr;
-    const int nb_item = 2 * p.nchunk_main + p.nchunk_sc;                 // batches per work item
     const int n_my_items = (p.num_items - item0 + item_stride - 1) / item_stride;
-    const int Q = n_my_items > 0 ? n_my_items * nb_item : 0;
-    float4 v0[4], v1[4];                       // the batch in flight: 4 rows x 8 channels of this thread
-    // batch q -> (tile, chunk, half); row slot i -> halo row, validity
-    auto batch_of = [&](int q, TileCoord& t, int& c, int& half) {
-      const int it = q / nb_item, w = q - it * nb_item;
+    const int Q = n_my_items > 0 ? n_my_items * nchunks : 0;             // chunks this CTA transforms (or skips: TMA)
+    constexpr int NR = 6;
+    float4 v0[NR], v1[NR];                     // the chunk in flight: 6 rows x 8 channels of this thread
+    auto chunk_of = [&](int q, TileCoord& t, int& c) {
+      const int it = q / nchunks;
+      c = q - it * nchunks;
       t = decode_tile<BN, PAIR>(p, item0 + it * item_stride, rank);
-      if (w < 2 * p.nchunk_main) { c = w >> 1; half = w & 1; } else { c = p.nchunk_main + (w - 2 * p.nchunk_main); half = 0; }
     };
-    auto row_of = [&](bool main, int half, int i, int& r, bool& valid) {
-      if (main) { r = r0 + 32 * (3 * half + i); valid = i < 3 && r < A_ROWS; }
-      else { const int idx = r0 + 32 * i; r = ((idx >> 3) + 1) * HALO_W + (idx & 7) + 1; valid = true; }
+    // row slot i of a chunk -> halo row (3x3: all 180 rows; 1x1: the 128 centre rows, always inside the image)
+    auto row_of = [&](bool main, int i, int& r, bool& valid) {
+      if (main) { r = r0 + 32 * i; valid = r < A_ROWS; }
+      else { const int idx = r0 + 32 * i; r = ((idx >> 3) + 1) * HALO_W + (idx & 7) + 1; valid = i < 4; }
     };
     auto issue = [&](int q) {
-      TileCoord t; int c, half;
-      batch_of(q, t, c, half);
+      TileCoord t; int c;
+      chunk_of(q, t, c);
       const bool main = c < p.nchunk_main;
       const XfOperand& src = main ? xf.a : xf.x;
       if (src.s1 == nullptr) return;
@@ -467,9 +476,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (cg < src.C1) { base = src.s1 + cg; ld = src.C1; } else { base = src.s2 + (cg - src.C1); ld = src.C2; }
       base += static_cast<size_t>(t.b) * p.H * p.W * ld + j * 8;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NR; ++i) {
         int r; bool valid;
-        row_of(main, half, i, r, valid);
+        row_of(main, i, r, valid);
         const int hy = r / HALO_W, hx = r - hy * HALO_W;
         const int h = t.h0 - 1 + hy, w = t.w0 - 1 + hx;
         v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i];
@@ -483,41 +492,42 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t aph = 0;
     int cur_b = -1;
     float vmax = 0.f;
-    auto process = [&](int q) {
-      TileCoord t; int c, half;
-      batch_of(q, t, c, half);
+    long long w_xe = 0, w_xp = 0;              // debug: cycles waiting for a free stage / preparing chunks
+    if (Q > 0) issue(0);
+#pragma unroll 1
+    for (int q = 0; q < Q; ++q) {
+      TileCoord t; int c;
+      chunk_of(q, t, c);
       const bool main = c < p.nchunk_main;
       const XfOperand& src = main ? xf.a : xf.x;
-      const bool first = half == 0, last = !main || half == 1;
-      if (first) {
-        if (norm_a && c == 0 && t.b != cur_b) {
-          // the scale / shift table of this batch element is built by warp 3 (below): release the old one, wait for the new
-          named_bar_sync(2, kXfWarps * 32 + 32);
-          named_bar_sync(3, kXfWarps * 32 + 32);
-          cur_b = t.b;
-        }
-        ptx::mbar_wait(a_empty(as), aph ^ 1u);
+      if (norm_a && c == 0 && t.b != cur_b) {
+        // the scale / shift table of this batch element is built by warp 3 (above): release the old one, wait for the new
+        named_bar_sync(2, kXfWarps * 32 + 32);
+        named_bar_sync(3, kXfWarps * 32 + 32);
+        cur_b = t.b;
       }
+      const long long tc0 = p.dbg ? clock64() : 0;
+      ptx::mbar_wait(a_empty(as), aph ^ 1u);
+      const long long tc1 = p.dbg ? clock64() : 0;
       if (src.s1 != nullptr) {
         const uint32_t stage = sA(as);
-        float4 sc0, sc1, sh0, sh1;
-        sc0 = sc1 = sh0 = sh1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (main && norm_a) {
-          const int cg = c * BK + j * 8;
-          sc0 = *reinterpret_cast<const float4*>(s_xsc + cg); sc1 = *reinterpret_cast<const float4*>(s_xsc + cg + 4);
-          sh0 = *reinterpret_cast<const float4*>(s_xsh + cg); sh1 = *reinterpret_cast<const float4*>(s_xsh + cg + 4);
-        }
+        const bool norm = main && norm_a;
+        const float* tsc = s_xsc + c * BK + j * 8;     // (only dereferenced when norm)
+        const float* tsh = s_xsh + c * BK + j * 8;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NR; ++i) {
           int r; bool valid;
-          row_of(main, half, i, r, valid);
+          row_of(main, i, r, valid);
           if (!valid) continue;
           const int hy = r / HALO_W, hx = r - hy * HALO_W;
           const int h = t.h0 - 1 + hy, w = t.w0 - 1 + hx;
           uint2 h0 = make_uint2(0u, 0u), l0 = h0, h1 = h0, l1 = h0;
           if (h >= 0 && h < p.H && w >= 0 && w < p.W) {          // zero padding of the ACTIVATED tensor outside the image
             float4 a0 = v0[i], a1 = v1[i];
-            if (main && norm_a) { a0 = norm_act(a0, sc0, sh0, xf.silu); a1 = norm_act(a1, sc1, sh1, xf.silu); }
+            if (norm) {
+              a0 = norm_act(a0, *reinterpret_cast<const float4*>(tsc), *reinterpret_cast<const float4*>(tsh), xf.silu);
+              a1 = norm_act(a1, *reinterpret_cast<const float4*>(tsc + 4), *reinterpret_cast<const float4*>(tsh + 4), xf.silu);
+            }
             split4(a0, h0, l0); split4(a1, h1, l1);
             vmax = amax4(a0, amax4(a1, vmax));
           }
@@ -526,17 +536,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::st_shared_v4(dst + A_PLANE_STRIDE, pack8(l0, l1));
         }
       }
-      if (q + 1 < Q) issue(q + 1);           // v0 / v1 are free again: next batch's loads fly during the fence / arrive / wait
-      if (last) {
-        if (src.s1 != nullptr) ptx::fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(a_full(as));
-        if (++as == A_STAGES) { as = 0; aph ^= 1u; }
-      }
-    };
-    if (Q > 0) issue(0);
-#pragma unroll 1
-    for (int q = 0; q < Q; ++q) process(q);
+      if (q + 1 < Q) issue(q + 1);             // v0 / v1 are free again: the next chunk's loads fly during the fence / arrive / wait
+      if (src.s1 != nullptr) ptx::fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(a_full(as));
+      if (++as == A_STAGES) { as = 0; aph ^= 1u; }
+      if (p.dbg) { w_xe += tc1 - tc0; w_xp += clock64() - tc1; }
+    }
+    if (p.dbg && xt == 0) { p.dbg[blockIdx.x * 8 + 6] = w_xe; p.dbg[blockIdx.x * 8 + 7] = w_xp; }
     if (vmax > kHalfMax && xf.overflow) atomicAdd(xf.overflow, 1ull);
   } else if (is_epi) {
     // ------------------------------------------------------------------ epilogue (8 warps)
@@ -809,9 +816,9 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
     }
     if (nl == 0) nl = 1;
     const double kb_per_cta = static_cast<double>(p.num_items) * (9.0 * p.nchunk_main + p.nchunk_sc) / nl;
-    fprintf(stderr, "[halo dbg] items=%d issuing ctas=%d kblocks/cta=%.0f (mma floor %.0f cyc) | issuer loop %.0f cyc: wait tmem %.0f, A %.0f, B %.0f | producer wait: A-free %.0f, B-free %.0f\n",
-            p.num_items, nl, kb_per_cta, kb_per_cta * 768.0 * (BN / 128.0), sum[0] / nl, sum[1] / nl, sum[2] / nl, sum[3] / nl,
-            sum[4] / nctas, sum[5] / nctas);
+    fprintf(stderr, "[halo dbg%s] items=%d issuing ctas=%d kblocks/cta=%.0f (mma floor %.0f cyc) | issuer loop %.0f cyc: wait tmem %.0f, A %.0f, B %.0f | producer wait: A-free %.0f, B-free %.0f | transform: stage wait %.0f, prepare %.0f\n",
+            XF ? " XF" : "", p.num_items, nl, kb_per_cta, kb_per_cta * 768.0 * (BN / 128.0), sum[0] / nl, sum[1] / nl, sum[2] / nl, sum[3] / nl,
+            sum[4] / nctas, sum[5] / nctas, sum[6] / nctas, sum[7] / nctas);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv_halo launch: ") + cudaGetErrorString(e); return 1; }

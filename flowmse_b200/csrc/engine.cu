@@ -195,7 +195,7 @@ struct flowse_ctx {
   // (|v| > 65504 saturates silently otherwise); read back through flowse_fp16_overflow
   unsigned long long* overflow = nullptr;
   int whole_graph = 1;                      // capture the whole sampler call as one CUDA graph (second call with the same schedule)
-  int fuse_prep = 1;                        // halo-kernel layers prepare their operands in the conv kernel (no standalone prep pass)
+  int fuse_prep = 2;                        // conv kernels prepare their own operands (no standalone prep pass): 1 halo layers, 2 all
 };
 
 namespace {
@@ -439,8 +439,13 @@ struct Builder {
     // warps, reading the fp32 activations directly.  A resampling block keeps its FIR prep for Conv_0 and for the shortcut
     // operand; its Conv_1 still normalises h1 itself.
     const bool resample = r.up || r.down;
-    const bool fuse0 = ctx->fuse_prep && !resample && conv_uses_halo(ctx, c0) && Cin <= 512;
-    const bool fuse1 = ctx->fuse_prep && conv_uses_halo(ctx, c1) && Co <= 512;
+    // fuse_prep 1: halo-kernel layers only; 2 (default): also the low-resolution layers on the per-tap kernel
+    auto can_fuse = [&](const ConvGemmArgs& c) {
+      if (conv_uses_halo(ctx, c)) return ctx->fuse_prep >= 1;
+      return ctx->fuse_prep >= 2 && ctx->conv_impl == 0 && c.Npad % 128 == 0;
+    };
+    const bool fuse0 = !resample && can_fuse(c0) && Cin <= 512;
+    const bool fuse1 = can_fuse(c1) && Co <= 512;
     if (fuse0) {
       c0.A = nullptr;
       c0.fA.s1 = s1; c0.fA.C1 = C1; c0.fA.s2 = s2; c0.fA.C2 = C2; c0.fA.qs1 = in1.qs; c0.fA.qs2 = in2 ? in2->qs : nullptr;
