@@ -65,6 +65,7 @@ class NCSNpp(nn.Module):
         self.all_modules = nn.ModuleList([_ParamHolder(spec.module_params(m)) for m in spec.module_list()])
         self._ctx = {}           # device index -> (Context, version stamp)
         self._stamp, self._sentinels = 0, None
+        self._packed_blob = None   # libflowse packed weights (checkpoint.load_packed): used instead of the fp32 parameters
         self._reset_like_reference(fourier_scale)
 
     def _reset_like_reference(self, fourier_scale):
@@ -105,7 +106,16 @@ class NCSNpp(nn.Module):
         self._stamp += 1
         self._sentinels = None
 
+    def load_packed_weights(self, blob):
+        """Use a libflowse packed-weights blob (``Context.export_packed``) as this backbone's weights.  The fp32
+        ``nn.Parameter`` tensors are NOT updated (the packed format is the deployment format; keep the fp32 checkpoint for
+        anything that needs ``state_dict``); a later ``load_state_dict`` switches back to the fp32 parameters."""
+        self._packed_blob = blob
+        self._stamp += 1
+        self._sentinels = None
+
     def _load_from_state_dict(self, *a, **k):
+        self._packed_blob = None
         self.invalidate()
         return super()._load_from_state_dict(*a, **k)
 
@@ -126,7 +136,10 @@ class NCSNpp(nn.Module):
             if ent is not None:
                 ent[0].close()
             ctx = new_context(dev)
-            ctx.load_state_dict({k: v for k, v in self.state_dict().items()})
+            if self._packed_blob is not None:
+                ctx.load_packed(self._packed_blob)
+            else:
+                ctx.load_state_dict({k: v for k, v in self.state_dict().items()})
             self._ctx[idx] = (ctx, ver)
             ent = self._ctx[idx]
         return ent[0]

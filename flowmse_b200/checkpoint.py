@@ -133,3 +133,25 @@ def unflatten_state_dict(blob: torch.Tensor) -> Dict[str, torch.Tensor]:
         off += k
     assert off == blob.numel()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Packed deployment checkpoints: the weights in libflowse's own layout (conv weights K-major fp16
+# hi/lo pairs, exactly what the tcgen05 kernels read) plus the hyper-parameters the inference path needs.
+# ---------------------------------------------------------------------------------------------------------------
+PACKED_FORMAT = "flowse-packed-v1"
+
+
+def save_packed(path: str, ctx, hparams: Optional[dict] = None) -> None:
+    """Write the weights held by a libflowse ``Context`` (EMA weights after ``model.eval()``) as a packed checkpoint."""
+    hp = dict(DEFAULT_HPARAMS)
+    hp.update(hparams or {})
+    hp.pop("data_module_cls", None)
+    torch.save({"format": PACKED_FORMAT, "hyper_parameters": hp, "blob": ctx.export_packed()}, path)
+
+
+def load_packed(path: str) -> dict:
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    if not isinstance(ck, dict) or ck.get("format") != PACKED_FORMAT:
+        raise ValueError(f"{path} is not a {PACKED_FORMAT} checkpoint")
+    return ck

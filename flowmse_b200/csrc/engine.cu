@@ -9,6 +9,7 @@
 #include "../../include/flowse.h"
 #include "flowse_internal.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -165,8 +166,12 @@ struct flowse_ctx {
   std::string err;
   bool weights_loaded = false;
   std::vector<ModSpec> mods;
-  // weights
-  std::vector<void*> dev_allocs;
+  // weights: every device buffer in upload order (the packed export / import walks this list), and the per-conv
+  // power-of-two weight scales in upload order
+  std::vector<std::pair<void*, size_t>> dev_allocs;
+  std::vector<float> conv_scales;
+  struct PackedSrc { const char* base; std::vector<unsigned long long> seg; std::vector<float> scales; size_t seg_i, scale_i, off; };
+  PackedSrc* packed = nullptr;              // set while flowse_load_packed rebuilds the weights from a packed blob
   TembWeights temb{};
   float *conv_in_w = nullptr, *conv_in_b = nullptr, *out_w = nullptr, *out_b = nullptr;
   std::map<int, RBW> rbs;
@@ -206,7 +211,9 @@ namespace {
 struct HostBlob {
   const float* base;
   std::unordered_map<std::string, std::pair<long long, long long>> idx;
+  const float* zeros = nullptr;     // packed import: the fp32 tensors are not available (nor needed), every lookup gets zeros
   const float* get(const std::string& name, long long numel, std::string* err) const {
+    if (zeros) return zeros;
     auto it = idx.find(name);
     if (it == idx.end()) { *err = "missing tensor '" + name + "'"; return nullptr; }
     if (it->second.second != numel) {
@@ -219,9 +226,19 @@ struct HostBlob {
 };
 
 int dev_upload(flowse_ctx* ctx, const void* host, size_t bytes, void** out) {
+  if (ctx->packed) {               // packed import: the next segment of the blob IS this buffer
+    auto* pk = ctx->packed;
+    if (pk->seg_i >= pk->seg.size() || pk->seg[pk->seg_i] != bytes) {
+      ctx->err = "packed weights: segment " + std::to_string(pk->seg_i) + " does not match this library's layout";
+      return 2;
+    }
+    host = pk->base + pk->off;
+    pk->off += (bytes + 255) & ~static_cast<size_t>(255);
+    ++pk->seg_i;
+  }
   void* d = nullptr;
   CK(cudaMalloc(&d, bytes));
-  ctx->dev_allocs.push_back(d);
+  ctx->dev_allocs.push_back({d, bytes});
   CK(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
   *out = d;
   return 0;
@@ -233,11 +250,21 @@ int up_f32(flowse_ctx* ctx, const float* host, size_t n, float** out) {
 int upload_conv(flowse_ctx* ctx, const float* w_main, int Cout, int Cin, int ntaps, const float* w_sc, int Cin2,
                 int Npad, ConvW* out) {
   const int K = ntaps * Cin + (w_sc ? Cin2 : 0);
+  out->Npad = Npad; out->K = K;
+  const size_t bytes = static_cast<size_t>(2) * Npad * K * sizeof(__half);
+  if (ctx->packed) {               // already in the K-major fp16 hi/lo format: no host-side packing
+    auto* pk = ctx->packed;
+    if (pk->scale_i >= pk->scales.size()) { ctx->err = "packed weights: conv scale list too short"; return 2; }
+    out->wscale_inv = pk->scales[pk->scale_i++];
+    ctx->conv_scales.push_back(out->wscale_inv);
+    return dev_upload(ctx, nullptr, bytes, reinterpret_cast<void**>(&out->wp));
+  }
   std::vector<__half> buf(static_cast<size_t>(2) * Npad * K);
   const int e = pack_conv_weights_host(w_main, Cout, Cin, ntaps, w_sc, Cin2, Npad, buf.data(),
                                        buf.data() + static_cast<size_t>(Npad) * K);
-  out->Npad = Npad; out->K = K; out->wscale_inv = std::ldexp(1.0f, -e);
-  return dev_upload(ctx, buf.data(), buf.size() * sizeof(__half), reinterpret_cast<void**>(&out->wp));
+  out->wscale_inv = std::ldexp(1.0f, -e);
+  ctx->conv_scales.push_back(out->wscale_inv);
+  return dev_upload(ctx, buf.data(), bytes, reinterpret_cast<void**>(&out->wp));
 }
 
 int load_weights_impl(flowse_ctx* ctx, const HostBlob& hb) {
@@ -754,7 +781,7 @@ void flowse_destroy(flowse_ctx* ctx) {
   if (ctx->plan) destroy_graphs(ctx->plan.get());
   if (ctx->overflow) cudaFree(ctx->overflow);
   if (ctx->arena) cudaFree(ctx->arena);
-  for (void* p : ctx->dev_allocs) cudaFree(p);
+  for (auto& p : ctx->dev_allocs) cudaFree(p.first);
   if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
   if (ctx->op_stats) cudaFree(ctx->op_stats);
   if (ctx->op_partials) cudaFree(ctx->op_partials);
@@ -780,6 +807,80 @@ int flowse_load_weights(flowse_ctx* ctx, const float* host_blob, const flowse_te
     hb.idx[std::string(nm)] = {descs[i].offset, descs[i].numel};
   }
   if (int rc = load_weights_impl(ctx, hb)) return rc;
+  CK(cudaDeviceSynchronize());
+  ctx->weights_loaded = true;
+  return 0;
+}
+
+// ---- packed weights: the context's device buffers - conv weights already in the K-major fp16 hi/lo
+// format, small tensors in fp32 - as one relocatable blob, so a deployment ships / loads them without the fp32 checkpoint
+// and without the host-side packing pass.
+namespace {
+constexpr unsigned long long kPackedMagic = 0x31304b5045534c46ull;    // "FLSEPK01"
+struct PackedHeader { unsigned long long magic; unsigned version, n_seg, n_conv, reserved; };
+size_t packed_payload_offset(unsigned n_seg, unsigned n_conv) {
+  const size_t h = sizeof(PackedHeader) + sizeof(unsigned long long) * n_seg + sizeof(float) * n_conv;
+  return (h + 255) & ~static_cast<size_t>(255);
+}
+}  // namespace
+
+size_t flowse_packed_bytes(flowse_ctx* ctx) {
+  if (!ctx || !ctx->weights_loaded) return 0;
+  size_t n = packed_payload_offset(static_cast<unsigned>(ctx->dev_allocs.size()), static_cast<unsigned>(ctx->conv_scales.size()));
+  for (auto& a : ctx->dev_allocs) n += (a.second + 255) & ~static_cast<size_t>(255);
+  return n;
+}
+
+int flowse_export_packed(flowse_ctx* ctx, void* host_out, size_t bytes) {
+  if (!ctx) return 2;
+  ctx->err.clear();
+  if (!ctx->weights_loaded) { ctx->err = "export_packed: weights not loaded"; return 2; }
+  if (!host_out || bytes < flowse_packed_bytes(ctx)) { ctx->err = "export_packed: buffer smaller than flowse_packed_bytes()"; return 2; }
+  CK(cudaSetDevice(ctx->device));
+  char* out = static_cast<char*>(host_out);
+  std::memset(out, 0, flowse_packed_bytes(ctx));
+  PackedHeader h{kPackedMagic, 1u, static_cast<unsigned>(ctx->dev_allocs.size()), static_cast<unsigned>(ctx->conv_scales.size()), 0u};
+  std::memcpy(out, &h, sizeof h);
+  auto* seg = reinterpret_cast<unsigned long long*>(out + sizeof h);
+  for (size_t i = 0; i < ctx->dev_allocs.size(); ++i) seg[i] = ctx->dev_allocs[i].second;
+  std::memcpy(out + sizeof h + sizeof(unsigned long long) * h.n_seg, ctx->conv_scales.data(), sizeof(float) * h.n_conv);
+  size_t off = packed_payload_offset(h.n_seg, h.n_conv);
+  for (auto& a : ctx->dev_allocs) {
+    CK(cudaMemcpy(out + off, a.first, a.second, cudaMemcpyDeviceToHost));
+    off += (a.second + 255) & ~static_cast<size_t>(255);
+  }
+  return 0;
+}
+
+int flowse_load_packed(flowse_ctx* ctx, const void* host_blob, size_t bytes) {
+  if (!ctx) return 2;
+  ctx->err.clear();
+  if (ctx->weights_loaded) { ctx->err = "weights already loaded; create a new context"; return 2; }
+  if (!host_blob || bytes < sizeof(PackedHeader)) { ctx->err = "load_packed: blob too small"; return 2; }
+  PackedHeader h;
+  std::memcpy(&h, host_blob, sizeof h);
+  if (h.magic != kPackedMagic || h.version != 1u) { ctx->err = "load_packed: not a libflowse packed-weights blob (magic / version)"; return 2; }
+  const size_t payload = packed_payload_offset(h.n_seg, h.n_conv);
+  if (h.n_seg > 100000u || h.n_conv > 100000u || bytes < payload) { ctx->err = "load_packed: truncated header"; return 2; }
+  flowse_ctx::PackedSrc pk;
+  pk.base = static_cast<const char*>(host_blob);
+  const auto* seg = reinterpret_cast<const unsigned long long*>(pk.base + sizeof h);
+  pk.seg.assign(seg, seg + h.n_seg);
+  const auto* sc = reinterpret_cast<const float*>(pk.base + sizeof h + sizeof(unsigned long long) * h.n_seg);
+  pk.scales.assign(sc, sc + h.n_conv);
+  pk.seg_i = 0; pk.scale_i = 0; pk.off = payload;
+  size_t need = payload;
+  unsigned long long biggest = 0;
+  for (auto v : pk.seg) { need += (v + 255) & ~static_cast<size_t>(255); biggest = std::max(biggest, v); }
+  if (bytes < need) { ctx->err = "load_packed: truncated payload"; return 2; }
+  CK(cudaSetDevice(ctx->device));
+  std::vector<float> zeros(static_cast<size_t>(9) * 512 * 512, 0.f);    // larger than any tensor of the backbone
+  HostBlob hb; hb.base = nullptr; hb.zeros = zeros.data();
+  ctx->packed = &pk;
+  const int rc = load_weights_impl(ctx, hb);
+  ctx->packed = nullptr;
+  if (rc) return rc;
+  if (pk.seg_i != pk.seg.size() || pk.scale_i != pk.scales.size()) { ctx->err = "load_packed: blob has more segments than this library's layout"; return 2; }
   CK(cudaDeviceSynchronize());
   ctx->weights_loaded = true;
   return 0;

@@ -59,6 +59,9 @@ def load_library():
     lib.flowse_op_attention.argtypes = [vp, i, vp, vp, i, i, i, vp]; lib.flowse_op_attention.restype = i
     lib.flowse_op_head_conv.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp]; lib.flowse_op_head_conv.restype = i
     lib.flowse_fp16_overflow.argtypes = [vp, C.POINTER(ll), i]; lib.flowse_fp16_overflow.restype = i
+    lib.flowse_packed_bytes.argtypes = [vp]; lib.flowse_packed_bytes.restype = C.c_size_t
+    lib.flowse_export_packed.argtypes = [vp, vp, C.c_size_t]; lib.flowse_export_packed.restype = i
+    lib.flowse_load_packed.argtypes = [vp, vp, C.c_size_t]; lib.flowse_load_packed.restype = i
     lib.flowse_stft_spec.argtypes = [vp, vp, ll, C.POINTER(i), i, i, f, f, vp, i, vp, vp]; lib.flowse_stft_spec.restype = i
     lib.flowse_spec_istft.argtypes = [vp, vp, i, C.POINTER(i), i, f, f, vp, vp, ll, vp]; lib.flowse_spec_istft.restype = i
     _lib = lib
@@ -70,7 +73,7 @@ EXPORTED_SYMBOLS = [
     "flowse_prior_sample", "flowse_ncsnpp_forward", "flowse_euler_step", "flowse_sample", "flowse_set_option",
     "flowse_kernel_launches", "flowse_profile_forward", "flowse_debug_tap", "flowse_debug_copy", "flowse_pack_conv_weights", "flowse_op_gn_prep",
     "flowse_op_conv_gemm", "flowse_op_attention", "flowse_stft_spec", "flowse_spec_istft", "flowse_op_head_conv",
-    "flowse_fp16_overflow",
+    "flowse_fp16_overflow", "flowse_packed_bytes", "flowse_export_packed", "flowse_load_packed",
 ]
 
 
@@ -134,6 +137,20 @@ class Context:
             off += n
         blob = torch.cat(parts).contiguous()
         self._check(self._lib.flowse_load_weights(self._h, blob.data_ptr(), descs, len(layout)))
+
+    def export_packed(self) -> torch.Tensor:
+        """The loaded weights in the library's own packed format (conv weights K-major fp16 hi/lo, small tensors fp32)
+        as a uint8 CPU tensor; ``load_packed`` on a fresh context restores them bit for bit."""
+        n = int(self._lib.flowse_packed_bytes(self._h))
+        if n == 0:
+            raise FlowseError("export_packed: no weights loaded")
+        blob = torch.empty(n, dtype=torch.uint8)
+        self._check(self._lib.flowse_export_packed(self._h, blob.data_ptr(), n))
+        return blob
+
+    def load_packed(self, blob: torch.Tensor):
+        blob = blob.detach().to(device="cpu", dtype=torch.uint8).contiguous()
+        self._check(self._lib.flowse_load_packed(self._h, blob.data_ptr(), blob.numel()))
 
     # ---- hot path ------------------------------------------------------------------------------
     def set_option(self, key: str, value: int):

@@ -153,6 +153,28 @@ class VFModel(nn.Module):
             model._ema_state = ckpt_io.backbone_state_from_checkpoint(ck, use_ema=True)
         return model
 
+    @classmethod
+    def load_from_packed(cls, path, **override):
+        """Build the model from a packed deployment checkpoint (``checkpoint.save_packed``): hyper-parameters as in
+        ``from_checkpoint_dict``, weights handed to libflowse in its own fp16 hi/lo layout (no fp32 tensors, no host-side
+        packing pass).  The result is for inference only."""
+        ck = ckpt_io.load_packed(path)
+        hp = dict(ck["hyper_parameters"])
+        hp.update({k: v for k, v in override.items() if k not in ("base_dir", "batch_size", "num_workers", "kwargs")})
+        allowed = {k: hp[k] for k in ("backbone", "ode", "t_eps", "T_rev", "sigma_min", "sigma_max", "n_fft",
+                                      "hop_length", "spec_factor", "spec_abs_exponent", "transform_type", "window")
+                   if k in hp}
+        model = cls(**allowed)
+        model.dnn.load_packed_weights(ck["blob"])
+        return model.eval()
+
+    def save_packed(self, path, device="cuda"):
+        """Write the LIVE weights (the EMA weights after ``eval()``) as a packed deployment checkpoint."""
+        dm = self.data_module
+        hp = dict(backbone="ncsnpp", ode="flowmatching", t_eps=self.t_eps, T_rev=self.T_rev, sigma_min=self.ode.sigma_min,
+                  sigma_max=self.ode.sigma_max, **dm.hparams())
+        ckpt_io.save_packed(path, self.flowse_context(device), hp)
+
     # ---- EMA swap, as VFModel.train/eval (model.py:92-106) --------------------------------------------------------
     def train(self, mode=True, no_ema=False):
         res = super().train(mode)

@@ -45,6 +45,17 @@ const char* flowse_last_error(const flowse_ctx* ctx);
  * K-major fp16 hi/lo format of the tcgen05 kernels and uploads them; synchronous. */
 int flowse_load_weights(flowse_ctx* ctx, const float* host_blob, const flowse_tensor_desc* descs, int n);
 
+/* Packed weights (the on-disk format either side of the path).  After flowse_load_weights the context
+ * holds the conv weights in the K-major fp16 hi/lo layout of the tcgen05 kernels (same bytes as fp32: 2 x 2 B) and the
+ * small tensors in fp32.  flowse_export_packed copies that state into a relocatable HOST blob of flowse_packed_bytes()
+ * bytes (header "FLSEPK01", segment sizes, per-conv power-of-two scales, 256-byte aligned segments);
+ * flowse_load_packed rebuilds a fresh context from such a blob without the fp32 checkpoint (torch_ema shadow_params,
+ * flowmse/model.py:81-106) and without the host-side packing pass.  Outputs are bit-identical to the fp32-loaded
+ * context.  A blob written by another library version (other segment layout) is rejected. */
+size_t flowse_packed_bytes(flowse_ctx* ctx);
+int flowse_export_packed(flowse_ctx* ctx, void* host_out, size_t bytes);
+int flowse_load_packed(flowse_ctx* ctx, const void* host_blob, size_t bytes);
+
 /* Bytes of device workspace the context holds for batch B, T frames (allocates the plan if needed). */
 size_t flowse_workspace_bytes(flowse_ctx* ctx, int B, int T);
 

@@ -260,3 +260,43 @@ def test_head_conv_op_vs_torch(ctx, shape):
     out = out.permute(0, 3, 1, 2).cpu().double()
     err = (out - ref).abs().max().item()
     assert err < 2e-5, err
+
+
+def test_packed_weights_round_trip(ctx, synthetic_sd, tmp_path):
+    """the weights exported in libflowse's packed layout (conv weights fp16 hi/lo) and loaded into a fresh
+    context / a fresh model give bit-identical outputs; damaged blobs are rejected."""
+    from flowmse_b200.lib import Context, FlowseError
+    from flowmse_b200.model import VFModel
+    blob = ctx.export_packed()
+    assert blob.dtype == torch.uint8 and 240e6 < blob.numel() < 300e6        # ~ the fp32 size: 2 x 2 B per conv weight
+    Y, z = _rand_c((1, 1, 256, 64), 101, 0.3).cuda(), _rand_c((1, 1, 256, 64), 102, np.sqrt(0.5)).cuda()
+    ts = torch.linspace(1.0, 0.03, 2)
+    ref = ctx.sample(Y, z, ts)
+    c2 = Context(0)
+    try:
+        c2.load_packed(blob)
+        assert torch.equal(torch.view_as_real(c2.sample(Y, z, ts)), torch.view_as_real(ref))
+        with pytest.raises(FlowseError):
+            c2.load_packed(blob)                                            # weights already loaded
+    finally:
+        c2.close()
+    for bad in (blob[:1000], torch.cat([torch.zeros(8, dtype=torch.uint8), blob[8:]]), blob[: blob.numel() // 2]):
+        c3 = Context(0)
+        try:
+            with pytest.raises(FlowseError):
+                c3.load_packed(bad)
+        finally:
+            c3.close()
+    # model level: save_packed / load_from_packed keep the hyper-parameters and the sampler output
+    model = VFModel(backbone="ncsnpp", ode="flowmatching", t_eps=0.04, sigma_max=0.5)
+    model.dnn.load_state_dict(synthetic_sd, strict=True)
+    model.eval()
+    path = str(tmp_path / "packed.ckpt")
+    model.save_packed(path)
+    m2 = VFModel.load_from_packed(path)
+    assert m2.t_eps == 0.04 and m2.ode.sigma_max == 0.5
+    torch.manual_seed(5)
+    a = model.enhance_spec(Y, N=2)
+    torch.manual_seed(5)
+    b = m2.enhance_spec(Y, N=2)
+    assert torch.equal(torch.view_as_real(a), torch.view_as_real(b))
