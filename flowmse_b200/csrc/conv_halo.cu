@@ -115,6 +115,7 @@ struct XfParams {
   const float* gamma; const float* beta; // GroupNorm affine of the main operand (over C1 + C2 channels)
   int silu;
   unsigned long long* overflow;
+  int dbg_mode;                          // measurement only (FLOWSE_XF_DBGMODE): 1 no global loads, 2 no math, 4 no smem stores
 };
 
 struct TileCoord { int b, h0, w0, n0; };
@@ -482,7 +483,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int hy = r / HALO_W, hx = r - hy * HALO_W;
         const int h = t.h0 - 1 + hy, w = t.w0 - 1 + hx;
         v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i];
-        if (valid && h >= 0 && h < p.H && w >= 0 && w < p.W) {
+        if (valid && h >= 0 && h < p.H && w >= 0 && w < p.W && !(xf.dbg_mode & 1)) {
           const float4* g = reinterpret_cast<const float4*>(base + (static_cast<size_t>(h) * p.W + w) * ld);
           v0[i] = __ldg(g); v1[i] = __ldg(g + 1);
         }
@@ -524,16 +525,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint2 h0 = make_uint2(0u, 0u), l0 = h0, h1 = h0, l1 = h0;
           if (h >= 0 && h < p.H && w >= 0 && w < p.W) {          // zero padding of the ACTIVATED tensor outside the image
             float4 a0 = v0[i], a1 = v1[i];
-            if (norm) {
-              a0 = norm_act(a0, *reinterpret_cast<const float4*>(tsc), *reinterpret_cast<const float4*>(tsh), xf.silu);
-              a1 = norm_act(a1, *reinterpret_cast<const float4*>(tsc + 4), *reinterpret_cast<const float4*>(tsh + 4), xf.silu);
+            if (xf.dbg_mode & 2) {
+              h0 = make_uint2(__float_as_uint(a0.x), __float_as_uint(a0.y)); l0 = make_uint2(__float_as_uint(a0.z), __float_as_uint(a0.w));
+              h1 = make_uint2(__float_as_uint(a1.x), __float_as_uint(a1.y)); l1 = make_uint2(__float_as_uint(a1.z), __float_as_uint(a1.w));
+            } else {
+              if (norm) {
+                a0 = norm_act(a0, *reinterpret_cast<const float4*>(tsc), *reinterpret_cast<const float4*>(tsh), xf.silu);
+                a1 = norm_act(a1, *reinterpret_cast<const float4*>(tsc + 4), *reinterpret_cast<const float4*>(tsh + 4), xf.silu);
+              }
+              split4(a0, h0, l0); split4(a1, h1, l1);
+              vmax = amax4(a0, amax4(a1, vmax));
             }
-            split4(a0, h0, l0); split4(a1, h1, l1);
-            vmax = amax4(a0, amax4(a1, vmax));
           }
           const uint32_t dst = stage + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
-          ptx::st_shared_v4(dst, pack8(h0, h1));
-          ptx::st_shared_v4(dst + A_PLANE_STRIDE, pack8(l0, l1));
+          if (!(xf.dbg_mode & 4)) {
+            ptx::st_shared_v4(dst, pack8(h0, h1));
+            ptx::st_shared_v4(dst + A_PLANE_STRIDE, pack8(l0, l1));
+          } else if (h0.x == 0x12345678u && l1.y == 0x9abcdef0u) {
+            ptx::st_shared_v4(dst, pack8(h0, h1));               // keeps the math alive without storing
+          }
         }
       }
       if (q + 1 < Q) issue(q + 1);             // v0 / v1 are free again: the next chunk's loads fly during the fence / arrive / wait
@@ -769,6 +779,8 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
     xf.x = XfOperand{a.fX.s1, a.fX.s2, a.fX.C1, a.fX.s2 ? a.fX.C2 : 0};
     xf.qs1 = a.fA.qs1; xf.qs2 = a.fA.qs2; xf.gamma = a.fA.gamma; xf.beta = a.fA.beta; xf.silu = a.fA.silu;
     xf.overflow = a.overflow;
+    static const int xf_dbg_mode = [] { const char* e = getenv("FLOWSE_XF_DBGMODE"); return e ? atoi(e) : 0; }();
+    xf.dbg_mode = xf_dbg_mode;
     auto bad = [&](const char* m) { if (err) *err = std::string("conv_halo (fused operand): ") + m; return 1; };
     if (a.fA.s1 && (xf.a.C1 + xf.a.C2 != a.Cin || xf.a.C1 % BK || a.Cin > kXfMaxC)) return bad("main operand channels");
     if (a.fA.s1 && a.fA.gamma && (!a.fA.beta || !a.fA.qs1 || (xf.a.C2 && !a.fA.qs2))) return bad("GroupNorm parameters / statistics missing");
