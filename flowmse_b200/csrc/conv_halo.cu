@@ -104,7 +104,7 @@ struct HaloParams {
   float* out;
   int div_sqrt2;
   double* qstats;
-  long long* dbg;   // optional per-CTA wait-cycle counters (FLOWSE_CONV_DBG=1): 8 per CTA
+  long long* dbg;   // optional per-CTA wait-cycle counters (FLOWSE_CONV_DBG=1): 16 per CTA
 };
 
 // fused operand sources (XF variant), device view of FusedOperand
@@ -305,7 +305,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      if (p.dbg) { p.dbg[blockIdx.x * 8 + 4] = w_pa; p.dbg[blockIdx.x * 8 + 5] = w_pb; }
+      if (p.dbg) { p.dbg[blockIdx.x * 16 + 4] = w_pa; p.dbg[blockIdx.x * 16 + 5] = w_pb; }
       if constexpr (PAIR) {
         // drain: every multicast commit aimed at this CTA's empty barriers has landed before the CTA may exit
         for (int i = 0; i < C::B_STAGES; ++i) {
@@ -383,8 +383,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         commit(t_full(buf));
       }
       if (p.dbg) {
-        p.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 1] = w_t;
-        p.dbg[blockIdx.x * 8 + 2] = w_a; p.dbg[blockIdx.x * 8 + 3] = w_b;
+        p.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin; p.dbg[blockIdx.x * 16 + 1] = w_t;
+        p.dbg[blockIdx.x * 16 + 2] = w_a; p.dbg[blockIdx.x * 16 + 3] = w_b;
       }
     }
   } else if (XF && warp == 3) {
@@ -494,6 +494,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int cur_b = -1;
     float vmax = 0.f;
     long long w_xe = 0, w_xp = 0;              // debug: cycles waiting for a free stage / preparing chunks
+    long long w_x1 = 0, w_x2 = 0, w_x3 = 0, w_x4 = 0;   // debug: rows, issue of the next chunk, proxy fence, arrive
     if (Q > 0) issue(0);
 #pragma unroll 1
     for (int q = 0; q < Q; ++q) {
@@ -546,14 +547,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      const long long tc2 = p.dbg ? clock64() : 0;
       if (q + 1 < Q) issue(q + 1);             // v0 / v1 are free again: the next chunk's loads fly during the fence / arrive / wait
+      const long long tc3 = p.dbg ? clock64() : 0;
       if (src.s1 != nullptr) ptx::fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      const long long tc4 = p.dbg ? clock64() : 0;
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(a_full(as));
       if (++as == A_STAGES) { as = 0; aph ^= 1u; }
-      if (p.dbg) { w_xe += tc1 - tc0; w_xp += clock64() - tc1; }
+      if (p.dbg) {
+        const long long tc5 = clock64();
+        w_xe += tc1 - tc0; w_xp += tc5 - tc1; w_x1 += tc2 - tc1; w_x2 += tc3 - tc2; w_x3 += tc4 - tc3; w_x4 += tc5 - tc4;
+      }
     }
-    if (p.dbg && xt == 0) { p.dbg[blockIdx.x * 8 + 6] = w_xe; p.dbg[blockIdx.x * 8 + 7] = w_xp; }
+    if (p.dbg && xt == 0) {
+      p.dbg[blockIdx.x * 16 + 6] = w_xe; p.dbg[blockIdx.x * 16 + 7] = w_xp; p.dbg[blockIdx.x * 16 + 8] = w_x1;
+      p.dbg[blockIdx.x * 16 + 9] = w_x2; p.dbg[blockIdx.x * 16 + 10] = w_x3; p.dbg[blockIdx.x * 16 + 11] = w_x4;
+    }
     if (vmax > kHalfMax && xf.overflow) atomicAdd(xf.overflow, 1ull);
   } else if (is_epi) {
     // ------------------------------------------------------------------ epilogue (8 warps)
@@ -813,24 +823,24 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   static const bool dbg = getenv("FLOWSE_CONV_DBG") != nullptr;
   long long* dbuf = nullptr;
   const size_t nctas = cfg.gridDim.x;
-  if (dbg) { cudaMalloc(&dbuf, nctas * 8 * sizeof(long long)); cudaMemset(dbuf, 0, nctas * 8 * sizeof(long long)); p.dbg = dbuf; }
+  if (dbg) { cudaMalloc(&dbuf, nctas * 16 * sizeof(long long)); cudaMemset(dbuf, 0, nctas * 16 * sizeof(long long)); p.dbg = dbuf; }
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, NMAIN, PAIR, XF>, tmA, tmX, tmW, p, xf);
   ++launch_counter();
   if (dbg) {
     cudaStreamSynchronize(s);
-    std::vector<long long> h(nctas * 8);
+    std::vector<long long> h(nctas * 16);
     cudaMemcpy(h.data(), dbuf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(dbuf);
-    double sum[8] = {0}; int nl = 0;
+    double sum[16] = {0}; int nl = 0;
     for (size_t c = 0; c < nctas; ++c) {
-      if (h[c * 8] > 0) ++nl;
-      for (int k = 0; k < 8; ++k) sum[k] += static_cast<double>(h[c * 8 + k]);
+      if (h[c * 16] > 0) ++nl;
+      for (int k = 0; k < 16; ++k) sum[k] += static_cast<double>(h[c * 16 + k]);
     }
     if (nl == 0) nl = 1;
     const double kb_per_cta = static_cast<double>(p.num_items) * (9.0 * p.nchunk_main + p.nchunk_sc) / nl;
-    fprintf(stderr, "[halo dbg%s] items=%d issuing ctas=%d kblocks/cta=%.0f (mma floor %.0f cyc) | issuer loop %.0f cyc: wait tmem %.0f, A %.0f, B %.0f | producer wait: A-free %.0f, B-free %.0f | transform: stage wait %.0f, prepare %.0f\n",
+    fprintf(stderr, "[halo dbg%s] items=%d issuing ctas=%d kblocks/cta=%.0f (mma floor %.0f cyc) | issuer loop %.0f cyc: wait tmem %.0f, A %.0f, B %.0f | producer wait: A-free %.0f, B-free %.0f | transform: stage wait %.0f, prepare %.0f (rows %.0f, issue next %.0f, proxy fence %.0f, arrive %.0f)\n",
             XF ? " XF" : "", p.num_items, nl, kb_per_cta, kb_per_cta * 768.0 * (BN / 128.0), sum[0] / nl, sum[1] / nl, sum[2] / nl, sum[3] / nl,
-            sum[4] / nctas, sum[5] / nctas, sum[6] / nctas, sum[7] / nctas);
+            sum[4] / nctas, sum[5] / nctas, sum[6] / nctas, sum[7] / nctas, sum[8] / nctas, sum[9] / nctas, sum[10] / nctas, sum[11] / nctas);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv_halo launch: ") + cudaGetErrorString(e); return 1; }

@@ -199,6 +199,7 @@ struct flowse_ctx {
   // sticky fp16 range flag: operand-producing kernels count the values whose magnitude exceeds the fp16 hi/lo range
   // (|v| > 65504 saturates silently otherwise); read back through flowse_fp16_overflow
   unsigned long long* overflow = nullptr;
+  double* rk_acc = nullptr;                 // device accumulator of flowse_rk_lincomb's error norm
   int whole_graph = 1;                      // capture the whole sampler call as one CUDA graph (second call with the same schedule)
   int fuse_prep = 2;                        // conv kernels prepare their own operands (no standalone prep pass): 1 halo layers, 2 all
 };
@@ -780,6 +781,7 @@ void flowse_destroy(flowse_ctx* ctx) {
   cudaDeviceSynchronize();
   if (ctx->plan) destroy_graphs(ctx->plan.get());
   if (ctx->overflow) cudaFree(ctx->overflow);
+  if (ctx->rk_acc) cudaFree(ctx->rk_acc);
   if (ctx->arena) cudaFree(ctx->arena);
   for (auto& p : ctx->dev_allocs) cudaFree(p.first);
   if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
@@ -1076,6 +1078,31 @@ int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const voi
     if (int rc = enqueue_sampler(ctx, ts, N, solver, sigma, own_prior, s, false)) return rc;
   CK(cudaMemcpyAsync(x_out, p->x, n * sizeof(float2), cudaMemcpyDeviceToDevice, s));
   CK(cudaGetLastError());
+  return 0;
+}
+
+int flowse_rk_lincomb(flowse_ctx* ctx, const void* base64, const void* K32, long long k_stride, const double* coef_host, int S,
+                      void* out64, void* out32, const void* ya64, const void* yb64, double rtol, double atol,
+                      double* sumsq_host, long long n, void* stream) {
+  if (!ctx) return 2;
+  ctx->err.clear();
+  if (n <= 0) return 0;
+  if (S < 0 || S > 8 || (S > 0 && (!K32 || !coef_host))) { ctx->err = "rk_lincomb: 0 <= S <= 8 stages with K and coefficients"; return 2; }
+  if (sumsq_host && (!ya64 || !yb64)) { ctx->err = "rk_lincomb: the scaled norm needs ya and yb"; return 2; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  if (sumsq_host) {
+    if (!ctx->rk_acc) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->rk_acc), sizeof(double)));
+    CK(cudaMemsetAsync(ctx->rk_acc, 0, sizeof(double), s));
+  }
+  launch_rk_lincomb(static_cast<const double2*>(base64), static_cast<const float2*>(K32), k_stride, coef_host, S,
+                    static_cast<double2*>(out64), static_cast<float2*>(out32), static_cast<const double2*>(ya64),
+                    static_cast<const double2*>(yb64), rtol, atol, sumsq_host ? ctx->rk_acc : nullptr, static_cast<size_t>(n), s);
+  CK(cudaGetLastError());
+  if (sumsq_host) {       // the step-size controller needs this number on the host: the one synchronisation per RK step
+    CK(cudaMemcpyAsync(sumsq_host, ctx->rk_acc, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
   return 0;
 }
 

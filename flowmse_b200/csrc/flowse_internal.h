@@ -68,6 +68,11 @@ void launch_axpy_c(const float2* a, const float2* b, float c, float2* out, size_
 void launch_heun_combine(const float2* x, const float2* v0, const float2* v1, float c, float2* out, size_t n,
                          cudaStream_t s);
 
+// v = base + sum_s coef[s] K[s] (complex128 state, complex64 stages): see rk_lincomb_kernel; sumsq must be zeroed
+void launch_rk_lincomb(const double2* base, const float2* K, long long k_stride, const double* coef, int S, double2* out64,
+                       float2* out32, const double2* ya, const double2* yb, double rtol, double atol, double* sumsq, size_t n,
+                       cudaStream_t s);
+
 // t_dev[0..B) = t; step_dev[0] = step (scalars passed as kernel arguments)
 void launch_set_scalars(float* t_dev, int B, float t, float* step_dev, float step, cudaStream_t s);
 // t_all[e*B + b] = times[e] for e < count <= 64 (the evaluation times of a sampler call, passed by value)

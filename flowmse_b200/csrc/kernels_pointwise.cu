@@ -80,6 +80,49 @@ heun_kernel(const float2* __restrict__ x, const float2* __restrict__ v0, const f
   }
 }
 
+// Adaptive Runge-Kutta building block (black-box RK45 solver, sampling/__init__.py:64-114 via scipy's solve_ivp):
+//   v = base + sum_s coef[s] * K[s]        base, v complex128; K[s] complex64 stage derivatives (promoted exactly)
+// optionally stored as complex128 (the integrator state) and / or rounded to complex64 (the next network input), and
+// optionally reduced to sum |v / (atol + rtol * max(|ya|, |yb|))|^2 (scipy's scaled RMS error norm before the sqrt / n).
+struct RkArgs {
+  const double2* base; const float2* K; long long k_stride; double coef[8]; int S;
+  double2* out64; float2* out32;
+  const double2* ya; const double2* yb; double rtol, atol; double* sumsq;
+};
+__global__ void __launch_bounds__(256)
+rk_lincomb_kernel(const RkArgs a, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  double local = 0.0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double2 v = a.base ? a.base[i] : make_double2(0.0, 0.0);
+    for (int s = 0; s < a.S; ++s) {
+      const float2 k = a.K[static_cast<size_t>(s) * a.k_stride + i];
+      v.x += a.coef[s] * static_cast<double>(k.x);
+      v.y += a.coef[s] * static_cast<double>(k.y);
+    }
+    if (a.out64) a.out64[i] = v;
+    if (a.out32) a.out32[i] = make_float2(static_cast<float>(v.x), static_cast<float>(v.y));
+    if (a.sumsq) {
+      const double2 p = a.ya[i], q = a.yb[i];
+      const double scale = a.atol + a.rtol * fmax(hypot(p.x, p.y), hypot(q.x, q.y));
+      const double m = hypot(v.x, v.y) / scale;
+      local += m * m;
+    }
+  }
+  if (a.sumsq) {
+    __shared__ double red[256];
+    red[threadIdx.x] = local;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(a.sumsq, red[0]);
+  }
+}
+
 __global__ void set_scalars_kernel(float* t_dev, int B, float t, float* step_dev, float step) {
   pdl_launch_dependents();
   pdl_wait();
@@ -425,6 +468,16 @@ softmax_rows_kernel(float* __restrict__ s, int rows, int cols) {
 
 void launch_set_scalars(float* t_dev, int B, float t, float* step_dev, float step, cudaStream_t s) {
   launch_k(set_scalars_kernel, dim3((B + 127) / 128), dim3(128), 0, s, t_dev, B, t, step_dev, step);
+}
+
+void launch_rk_lincomb(const double2* base, const float2* K, long long k_stride, const double* coef, int S, double2* out64,
+                       float2* out32, const double2* ya, const double2* yb, double rtol, double atol, double* sumsq, size_t n,
+                       cudaStream_t s) {
+  RkArgs a{};
+  a.base = base; a.K = K; a.k_stride = k_stride; a.S = S;
+  for (int i = 0; i < S && i < 8; ++i) a.coef[i] = coef[i];
+  a.out64 = out64; a.out32 = out32; a.ya = ya; a.yb = yb; a.rtol = rtol; a.atol = atol; a.sumsq = sumsq;
+  launch_k(rk_lincomb_kernel, dim3(grid_for(n)), dim3(256), 0, s, a, n);
 }
 
 void launch_set_times(float* t_all, int B, const float* times_host, int count, cudaStream_t s) {

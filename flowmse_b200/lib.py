@@ -59,6 +59,9 @@ def load_library():
     lib.flowse_op_attention.argtypes = [vp, i, vp, vp, i, i, i, vp]; lib.flowse_op_attention.restype = i
     lib.flowse_op_head_conv.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp]; lib.flowse_op_head_conv.restype = i
     lib.flowse_fp16_overflow.argtypes = [vp, C.POINTER(ll), i]; lib.flowse_fp16_overflow.restype = i
+    lib.flowse_rk_lincomb.argtypes = [vp, vp, vp, ll, C.POINTER(C.c_double), i, vp, vp, vp, vp, C.c_double, C.c_double,
+                                      C.POINTER(C.c_double), ll, vp]
+    lib.flowse_rk_lincomb.restype = i
     lib.flowse_packed_bytes.argtypes = [vp]; lib.flowse_packed_bytes.restype = C.c_size_t
     lib.flowse_export_packed.argtypes = [vp, vp, C.c_size_t]; lib.flowse_export_packed.restype = i
     lib.flowse_load_packed.argtypes = [vp, vp, C.c_size_t]; lib.flowse_load_packed.restype = i
@@ -73,7 +76,7 @@ EXPORTED_SYMBOLS = [
     "flowse_prior_sample", "flowse_ncsnpp_forward", "flowse_euler_step", "flowse_sample", "flowse_set_option",
     "flowse_kernel_launches", "flowse_profile_forward", "flowse_debug_tap", "flowse_debug_copy", "flowse_pack_conv_weights", "flowse_op_gn_prep",
     "flowse_op_conv_gemm", "flowse_op_attention", "flowse_stft_spec", "flowse_spec_istft", "flowse_op_head_conv",
-    "flowse_fp16_overflow", "flowse_packed_bytes", "flowse_export_packed", "flowse_load_packed",
+    "flowse_fp16_overflow", "flowse_rk_lincomb", "flowse_packed_bytes", "flowse_export_packed", "flowse_load_packed",
 ]
 
 
@@ -155,6 +158,21 @@ class Context:
     # ---- hot path ------------------------------------------------------------------------------
     def set_option(self, key: str, value: int):
         self._check(self._lib.flowse_set_option(self._h, key.encode(), int(value)))
+
+    def rk_lincomb(self, base64, K32, coef, out64=None, out32=None, norm_of=None, rtol=0.0, atol=0.0):
+        """v = base64 + sum_s coef[s] * K32[s] (complex128 state, complex64 stages K32 [S_max, ...]); optionally written to
+        out64 / out32 and, with norm_of = (ya64, yb64), reduced to sum |v / (atol + rtol max(|ya|, |yb|))|^2 (returned;
+        synchronises).  Tensors are CUDA, contiguous; the stage count is len(coef)."""
+        S = len(coef)
+        ref = base64 if base64 is not None else K32[0]
+        n = ref.numel()
+        arr = (C.c_double * max(S, 1))(*[float(c) for c in coef])
+        acc = C.c_double(0.0)
+        ya, yb = norm_of if norm_of is not None else (None, None)
+        self._check(self._lib.flowse_rk_lincomb(self._h, _ptr(base64), _ptr(K32), K32[0].numel() if K32 is not None else 0,
+                                                arr, S, _ptr(out64), _ptr(out32), _ptr(ya), _ptr(yb), float(rtol),
+                                                float(atol), C.byref(acc) if norm_of is not None else None, n, _stream()))
+        return acc.value if norm_of is not None else None
 
     def fp16_overflow(self, reset: bool = True) -> int:
         """Operand values seen outside the fp16 hi/lo range since the last reset (0 = the fp32-parity claim holds).

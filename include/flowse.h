@@ -86,6 +86,16 @@ int flowse_euler_step(flowse_ctx* ctx, const void* x, const void* v, float steps
 int flowse_sample(flowse_ctx* ctx, const void* y, const void* y_prior, const void* z, const float* timesteps_host, int N, int solver,
                   float sigma, void* x_out, int B, int T, void* stream);
 
+/* Building block of the adaptive black-box solver (replaces the NumPy arithmetic scipy's solve_ivp RK45 does on the host
+ * for get_black_box_solver, flowmse/sampling/__init__.py:64-114, with a device<->host round trip per network evaluation):
+ *   v = base + sum_{s<S} coef[s] * K[s]     base / v complex128 [n] (NULL base = 0), K complex64 [S][k_stride] (exact in fp64)
+ * out64 (complex128) / out32 (complex64, round-to-nearest) receive v when not NULL.  When sumsq_host != NULL the call also
+ * returns sum_i |v_i / (atol + rtol * max(|ya_i|, |yb_i|))|^2 (scipy's scaled error norm is sqrt(that / n)) and
+ * synchronises the stream - the single host round trip of an RK step.  coef_host: HOST doubles, S <= 8. */
+int flowse_rk_lincomb(flowse_ctx* ctx, const void* base64, const void* K32, long long k_stride, const double* coef_host, int S,
+                      void* out64, void* out32, const void* ya64, const void* yb64, double rtol, double atol,
+                      double* sumsq_host, long long n, void* stream);
+
 /* Sticky fp16-range flag.  Conv operands travel as fp16 hi/lo pairs (5 exponent bits): a value with |v| > 65504 - only
  * possible for the un-normalised shortcut operand of a ResBlock (layerspp.py:268-270) with pathological weights - would
  * saturate.  The operand-producing kernels count such values; *count receives the number of detections since the last

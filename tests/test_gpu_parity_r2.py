@@ -300,3 +300,61 @@ def test_packed_weights_round_trip(ctx, synthetic_sd, tmp_path):
     torch.manual_seed(5)
     b = m2.enhance_spec(Y, N=2)
     assert torch.equal(torch.view_as_real(a), torch.view_as_real(b))
+
+
+def test_rk_lincomb_kernel_vs_numpy(ctx):
+    """flowse_rk_lincomb: complex128 state + complex64 stages, outputs and the scaled squared norm vs NumPy."""
+    g = torch.Generator().manual_seed(17)
+    n, S = 70001, 5
+    base = torch.view_as_complex(torch.randn(n, 2, generator=g, dtype=torch.float64))
+    K = torch.view_as_complex(torch.randn(7, n, 2, generator=g))
+    ya = torch.view_as_complex(torch.randn(n, 2, generator=g, dtype=torch.float64))
+    coef = [0.3, -1.25, 0.0, 2.0, 1e-3]
+    out64 = torch.empty(n, dtype=torch.complex128, device="cuda")
+    out32 = torch.empty(n, dtype=torch.complex64, device="cuda")
+    ss = ctx.rk_lincomb(base.cuda(), K.cuda(), coef, out64=out64, out32=out32, norm_of=(ya.cuda(), base.cuda()), rtol=1e-3,
+                        atol=1e-4)
+    ref = base.numpy() + sum(c * K[s].numpy().astype(np.complex128) for s, c in enumerate(coef))
+    assert np.abs(out64.cpu().numpy() - ref).max() < 1e-13
+    assert np.array_equal(out32.cpu().numpy(), ref.astype(np.complex64))
+    scale = 1e-4 + 1e-3 * np.maximum(np.abs(ya.numpy()), np.abs(base.numpy()))
+    assert abs(ss - float(np.sum(np.abs(ref / scale) ** 2))) <= 1e-9 * ss
+    # no base, no outputs: only the norm
+    ss2 = ctx.rk_lincomb(None, K.cuda(), [1.0], norm_of=(ya.cuda(), ya.cuda()), rtol=0.0, atol=1.0)
+    assert abs(ss2 - float(np.sum(np.abs(K[0].numpy().astype(np.complex128)) ** 2))) <= 1e-9 * ss2
+
+
+def test_black_box_rk45_vs_scipy_oracle(synthetic_sd):
+    """get_black_box_solver (RK45 on the device) against scipy's solve_ivp driving the CPU oracle's vector field - the
+    reference's own construction (sampling/__init__.py:64-114) - on a [1,1,256,64] spectrogram: same number of function
+    evaluations (every accept / reject decision agrees) and the same sample within the north-star tolerance."""
+    from scipy import integrate
+    from flowmse_b200.model import VFModel
+    from flowmse_b200.sampling import get_black_box_solver
+    rtol = atol = 1e-3
+    model = VFModel(backbone="ncsnpp", ode="flowmatching")
+    model.dnn.load_state_dict(synthetic_sd, strict=True)
+    model.eval()
+    Y = _rand_c((1, 1, 256, 64), 111, 0.3)
+    torch.manual_seed(4321)
+    x, nfe = get_black_box_solver(model.ode, model, Y.cuda(), rtol=rtol, atol=atol, T_rev=1.0, t_eps=0.03)()
+    torch.manual_seed(4321)
+    z = torch.randn_like(Y.cuda()).cpu()                      # the prior draw the solver made
+    x0 = orc.prior_sample(Y, z)
+    torch.set_num_threads(os.cpu_count() or 1)
+
+    def ode_func(t, flat):
+        xt = torch.from_numpy(flat.reshape(tuple(Y.shape))).type(torch.complex64)
+        with torch.no_grad():
+            return orc.vf_forward(synthetic_sd, xt, torch.ones(1) * t, Y).numpy().reshape(-1)
+
+    sol = integrate.solve_ivp(ode_func, (1.0, 0.03), x0.numpy().reshape(-1), rtol=rtol, atol=atol, method="RK45")
+    x_ref = torch.tensor(sol.y[:, -1]).reshape(Y.shape).type(torch.complex64)
+    frac, mx = _sep(x, x_ref)
+    _record("black_box_rk45_T64", dict(rtol=rtol, atol=atol, nfe_device=nfe, nfe_scipy=int(sol.nfev), frac_outside=frac, max_abs=mx))
+    assert nfe == sol.nfev, (nfe, sol.nfev)
+    assert frac <= 1e-4 and mx < 1e-3, (frac, mx)
+    # any other scipy method takes the reference's host route and still works with the B200 vector field
+    torch.manual_seed(4321)
+    x2, nfe2 = get_black_box_solver(model.ode, model, Y.cuda(), rtol=1e-2, atol=1e-2, method="RK23")()
+    assert x2.shape == Y.shape and nfe2 > 0 and torch.isfinite(torch.view_as_real(x2)).all()
