@@ -374,78 +374,87 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
     if constexpr (XF) {
       // -------------------------------------------------------------- operand transform (the epilogue warps, XF only)
-      // K block kb = (tap, 64-channel chunk): 128 tile rows x 8 sixteen-byte columns = 4 rows per thread.  The loads of
-      // block kb + 1 are issued as soon as block kb has been consumed, before the wait for its shared-memory stage.
+      // K block kb = (tap, 64-channel chunk): 128 tile rows x 8 sixteen-byte columns = 4 rows per thread.  All rows of
+      // all K blocks of this CTA form one stream walked by a ROLLED loop (one row per trip) with the global loads kAhead
+      // rows in front of the row being prepared - same scheme and same reason (instruction-cache footprint) as in
+      // conv_halo.cu.
       const int xt = static_cast<int>(threadIdx.x) - 64;     // 0..255
       const int j = xt & 7, rr0 = xt >> 3;
       const bool norm_a = xf.a.s1 != nullptr && xf.gamma != nullptr;
-      float4 v0[4], v1[4];
-      bool inb[4];
-      auto issue = [&](int kb) {
-        const bool main = kb < nkb_main;
+      auto kb_fused = [&](int kb) { return (kb < nkb_main ? xf.a.s1 : xf.x.s1) != nullptr; };
+      auto rows_of = [&](int kb) { return kb_fused(kb) ? 4 : 1; };          // TMA-fed K block: one empty slot
+      struct Cur { int kb, i; };
+      auto advance = [&](Cur& k) { if (++k.i == rows_of(k.kb)) { k.i = 0; ++k.kb; } };
+      // meta: bits 0..15 tile row, bit 16 row exists, bit 17 pixel inside the image
+      auto fetch = [&](const Cur& k, float4& a0, float4& a1, int& meta) {
+        a0 = make_float4(0.f, 0.f, 0.f, 0.f); a1 = a0; meta = 0;
+        if (k.kb >= kb_end || !kb_fused(k.kb)) return;
+        const bool main = k.kb < nkb_main;
         const XfOperand& src = main ? xf.a : xf.x;
-        if (src.s1 == nullptr) return;
-        int dy = 0, dx = 0, ch = kb - nkb_main;
+        int dy = 0, dx = 0, ch = k.kb - nkb_main;
         if (main) {
-          const int tap = kb / p.nchunk_main;
-          ch = kb - tap * p.nchunk_main;
+          const int tap = k.kb / p.nchunk_main;
+          ch = k.kb - tap * p.nchunk_main;
           if (p.ntaps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
         }
+        const int r = rr0 + 32 * k.i;
+        const int h = h0 + (r >> xf.tw_shift) + dy, w = w0 + (r & (p.TW - 1)) + dx;
+        const bool inb = h >= 0 && h < p.H && w >= 0 && w < p.W;   // outside: zero padding (what TMA's OOB fill delivers)
+        meta = r | (1 << 16) | (inb ? (1 << 17) : 0);
+        if (!inb) return;
         const int cg = ch * BK;
         const float* base; int ld;
         if (cg < src.C1) { base = src.s1 + cg; ld = src.C1; } else { base = src.s2 + (cg - src.C1); ld = src.C2; }
-        base += static_cast<size_t>(b) * p.H * p.W * ld + j * 8;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = rr0 + 32 * i;
-          const int h = h0 + (r >> xf.tw_shift) + dy, w = w0 + (r & (p.TW - 1)) + dx;
-          inb[i] = h >= 0 && h < p.H && w >= 0 && w < p.W;       // outside: zero padding (what TMA's OOB fill delivers)
-          v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i];
-          if (inb[i]) {
-            const float4* g = reinterpret_cast<const float4*>(base + (static_cast<size_t>(h) * p.W + w) * ld);
-            v0[i] = __ldg(g); v1[i] = __ldg(g + 1);
-          }
-        }
+        const float4* g = reinterpret_cast<const float4*>(
+            base + (static_cast<size_t>(b) * p.H * p.W + static_cast<size_t>(h) * p.W + w) * ld + j * 8);
+        a0 = __ldg(g); a1 = __ldg(g + 1);
       };
+      constexpr int kAhead = 4;                // rows in flight per thread: one whole K block
+      float4 qa[kAhead], qb[kAhead];
+      int qm[kAhead];
+      Cur L{kb_begin, 0}, P{kb_begin, 0};
+#pragma unroll
+      for (int d = 0; d < kAhead; ++d) { fetch(L, qa[d], qb[d], qm[d]); advance(L); }
+      if (norm_a) asm volatile("bar.sync 2, 288;" ::: "memory");   // scale / shift table (built by warp 1) is complete
       float vmax = 0.f;
       int stage = 0;
       uint32_t phase = 0;
-      if (kb_begin < kb_end) issue(kb_begin);
-      if (norm_a) asm volatile("bar.sync 2, 288;" ::: "memory");   // scale / shift table (built by warp 1) is complete
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const bool main = kb < nkb_main;
-        const XfOperand& src = main ? xf.a : xf.x;
-        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-        if (src.s1 != nullptr) {
-          const uint32_t sA_hi = smem_base + stage * C::STAGE_BYTES;
-          float4 sc0, sc1, sh0, sh1;
-          sc0 = sc1 = sh0 = sh1 = make_float4(0.f, 0.f, 0.f, 0.f);
-          const bool norm = main && norm_a;
-          if (norm) {
-            const int cg = (kb % p.nchunk_main) * BK + j * 8;
-            sc0 = *reinterpret_cast<const float4*>(s_xsc + cg); sc1 = *reinterpret_cast<const float4*>(s_xsc + cg + 4);
-            sh0 = *reinterpret_cast<const float4*>(s_xsh + cg); sh1 = *reinterpret_cast<const float4*>(s_xsh + cg + 4);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = rr0 + 32 * i;
-            uint2 hh0 = make_uint2(0u, 0u), ll0 = hh0, hh1 = hh0, ll1 = hh0;
-            if (inb[i]) {
-              float4 a0 = v0[i], a1 = v1[i];
-              if (norm) { a0 = norm_act(a0, sc0, sh0, xf.silu); a1 = norm_act(a1, sc1, sh1, xf.silu); }
-              split4(a0, hh0, ll0); split4(a1, hh1, ll1);
-              vmax = amax4(a0, amax4(a1, vmax));
+#pragma unroll 1
+      while (P.kb < kb_end) {
+        const bool main = P.kb < nkb_main;
+        const bool fused = kb_fused(P.kb);
+        if (P.i == 0) ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+        const int meta = qm[0];
+        if (meta & (1 << 16)) {
+          const int r = meta & 0xffff;
+          uint2 hh0 = make_uint2(0u, 0u), ll0 = hh0, hh1 = hh0, ll1 = hh0;
+          if (meta & (1 << 17)) {
+            float4 a0 = qa[0], a1 = qb[0];
+            if (main && norm_a) {
+              const float* tsc = s_xsc + (P.kb % p.nchunk_main) * BK + j * 8;
+              const float* tsh = s_xsh + (P.kb % p.nchunk_main) * BK + j * 8;
+              a0 = norm_act(a0, *reinterpret_cast<const float4*>(tsc), *reinterpret_cast<const float4*>(tsh), xf.silu);
+              a1 = norm_act(a1, *reinterpret_cast<const float4*>(tsc + 4), *reinterpret_cast<const float4*>(tsh + 4), xf.silu);
             }
-            const uint32_t dst = sA_hi + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
-            ptx::st_shared_v4(dst, pack8(hh0, hh1));
-            ptx::st_shared_v4(dst + A_BYTES, pack8(ll0, ll1));
+            split4(a0, hh0, ll0); split4(a1, hh1, ll1);
+            vmax = amax4(a0, amax4(a1, vmax));
           }
+          const uint32_t dst = smem_base + stage * C::STAGE_BYTES + static_cast<uint32_t>(r) * 128u +
+                               (static_cast<uint32_t>(j ^ (r & 7)) << 4);
+          ptx::st_shared_v4(dst, pack8(hh0, hh1));
+          ptx::st_shared_v4(dst + A_BYTES, pack8(ll0, ll1));
         }
-        if (kb + 1 < kb_end) issue(kb + 1);
-        if (src.s1 != nullptr) ptx::fence_proxy_async();     // generic-proxy stores -> visible to the tensor core's reads
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(full_bar(stage));
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+#pragma unroll
+        for (int d = 0; d + 1 < kAhead; ++d) { qa[d] = qa[d + 1]; qb[d] = qb[d + 1]; qm[d] = qm[d + 1]; }
+        fetch(L, qa[kAhead - 1], qb[kAhead - 1], qm[kAhead - 1]);
+        advance(L);
+        if (P.i + 1 == rows_of(P.kb)) {                    // last row of the K block: hand the stage to the MMA warp
+          if (fused) ptx::fence_proxy_async();             // generic-proxy stores -> visible to the tensor core's reads
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(full_bar(stage));
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        advance(P);
       }
       if (vmax > kHalfMax && xf.overflow) atomicAdd(xf.overflow, 1ull);
     }

@@ -115,7 +115,6 @@ struct XfParams {
   const float* gamma; const float* beta; // GroupNorm affine of the main operand (over C1 + C2 channels)
   int silu;
   unsigned long long* overflow;
-  int dbg_mode;                          // measurement only (FLOWSE_XF_DBGMODE): 1 no global loads, 2 no math, 4 no smem stores
 };
 
 struct TileCoord { int b, h0, w0, n0; };
@@ -444,126 +443,114 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (is_xf) {
     // ------------------------------------------------------------------ operand transform (warps 12..19, XF only)
-    // Work unit = one 64-channel chunk: 6 operand rows per thread for a 3x3 chunk (180 halo rows), 4 for a 1x1 shortcut
-    // chunk (128 centre rows).  ALL global loads of chunk c+1 (48 KB per SM) are issued as soon as chunk c has been
-    // consumed, before the wait for the next free operand stage: the transform runs ahead of the tensor core, so the
-    // HBM latency under load (several microseconds) hides behind that wait, like the TMA prefetch of the halo it replaces.
+    // A thread owns one 16-byte column (8 channels) of every 32nd operand row: 6 rows of a 3x3 chunk (180 halo rows), 4 of
+    // a 1x1 shortcut chunk (its 128 centre rows).  The rows of all chunks of all tiles form ONE stream that is walked by
+    // a ROLLED loop - one row per trip, ~150 instructions - with the global loads running kAhead rows in front of the row
+    // being normalised / split / stored (values rotate through registers).  Keeping this loop small matters as much as
+    // the prefetch: an unrolled version of the same work made the kernel 80 KB of SASS, and the transform warps then ran
+    // at a tenth of their issue rate on instruction-cache misses (profiles/README.md, round 2).
     const int xt = static_cast<int>(threadIdx.x) - w_xf0 * 32;            // 0..255
     const int j = xt & 7;                      // 16-byte column of the 128-byte operand row: channels 8j .. 8j+7 of the chunk
     const int r0 = xt >> 3;                    // rows r0 + 32 i
     const bool norm_a = xf.a.s1 != nullptr && xf.gamma != nullptr;
-    const int n_my_items = (p.num_items - item0 + item_stride - 1) / item_stride;
-    const int Q = n_my_items > 0 ? n_my_items * nchunks : 0;             // chunks this CTA transforms (or skips: TMA)
-    constexpr int NR = 6;
-    float4 v0[NR], v1[NR];                     // the chunk in flight: 6 rows x 8 channels of this thread
-    auto chunk_of = [&](int q, TileCoord& t, int& c) {
-      const int it = q / nchunks;
-      c = q - it * nchunks;
-      t = decode_tile<BN, PAIR>(p, item0 + it * item_stride, rank);
-    };
-    // row slot i of a chunk -> halo row (3x3: all 180 rows; 1x1: the 128 centre rows, always inside the image)
-    auto row_of = [&](bool main, int i, int& r, bool& valid) {
-      if (main) { r = r0 + 32 * i; valid = r < A_ROWS; }
-      else { const int idx = r0 + 32 * i; r = ((idx >> 3) + 1) * HALO_W + (idx & 7) + 1; valid = i < 4; }
-    };
-    auto issue = [&](int q) {
-      TileCoord t; int c;
-      chunk_of(q, t, c);
-      const bool main = c < p.nchunk_main;
-      const XfOperand& src = main ? xf.a : xf.x;
-      if (src.s1 == nullptr) return;
-      const int cg = (main ? c : c - p.nchunk_main) * BK;
-      const float* base; int ld;
-      if (cg < src.C1) { base = src.s1 + cg; ld = src.C1; } else { base = src.s2 + (cg - src.C1); ld = src.C2; }
-      base += static_cast<size_t>(t.b) * p.H * p.W * ld + j * 8;
-#pragma unroll
-      for (int i = 0; i < NR; ++i) {
-        int r; bool valid;
-        row_of(main, i, r, valid);
-        const int hy = r / HALO_W, hx = r - hy * HALO_W;
-        const int h = t.h0 - 1 + hy, w = t.w0 - 1 + hx;
-        v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i];
-        if (valid && h >= 0 && h < p.H && w >= 0 && w < p.W && !(xf.dbg_mode & 1)) {
-          const float4* g = reinterpret_cast<const float4*>(base + (static_cast<size_t>(h) * p.W + w) * ld);
-          v0[i] = __ldg(g); v1[i] = __ldg(g + 1);
+    const int n_my_items = item0 < p.num_items ? (p.num_items - item0 + item_stride - 1) / item_stride : 0;
+    // position in the row stream: work item ordinal, chunk, row slot (+ the tile of that item)
+    struct Cur { int it, c, i; TileCoord t; };
+    auto chunk_fused = [&](int c) { return (c < p.nchunk_main ? xf.a.s1 : xf.x.s1) != nullptr; };
+    auto rows_of = [&](int c) { return !chunk_fused(c) ? 1 : (c < p.nchunk_main ? 6 : 4); };   // TMA-fed chunk: one empty slot
+    auto advance = [&](Cur& k) {
+      if (++k.i == rows_of(k.c)) {
+        k.i = 0;
+        if (++k.c == nchunks) {
+          k.c = 0;
+          if (++k.it < n_my_items) k.t = decode_tile<BN, PAIR>(p, item0 + k.it * item_stride, rank);
         }
       }
     };
+    // meta: bits 0..15 operand row, bit 16 row exists, bit 17 pixel inside the image
+    auto fetch = [&](const Cur& k, float4& a0, float4& a1, int& meta) {
+      a0 = make_float4(0.f, 0.f, 0.f, 0.f); a1 = a0; meta = 0;
+      if (k.it >= n_my_items || !chunk_fused(k.c)) return;
+      const bool main = k.c < p.nchunk_main;
+      const XfOperand& src = main ? xf.a : xf.x;
+      const int slot = r0 + 32 * k.i;
+      const int r = main ? slot : ((slot >> 3) + 1) * HALO_W + (slot & 7) + 1;
+      if (r >= A_ROWS) return;
+      const int hy = r / HALO_W, hx = r - hy * HALO_W;
+      const int h = k.t.h0 - 1 + hy, w = k.t.w0 - 1 + hx;
+      const bool inb = h >= 0 && h < p.H && w >= 0 && w < p.W;
+      meta = r | (1 << 16) | (inb ? (1 << 17) : 0);
+      if (!inb) return;
+      const int cg = (main ? k.c : k.c - p.nchunk_main) * BK;
+      const float* base; int ld;
+      if (cg < src.C1) { base = src.s1 + cg; ld = src.C1; } else { base = src.s2 + (cg - src.C1); ld = src.C2; }
+      const float4* g = reinterpret_cast<const float4*>(
+          base + (static_cast<size_t>(k.t.b) * p.H * p.W + static_cast<size_t>(h) * p.W + w) * ld + j * 8);
+      a0 = __ldg(g); a1 = __ldg(g + 1);
+    };
+    constexpr int kAhead = 3;                  // rows in flight per thread (24 KB per SM)
+    float4 qa[kAhead], qb[kAhead];
+    int qm[kAhead];
+    Cur L{0, 0, 0, TileCoord{0, 0, 0, 0}};
+    if (n_my_items > 0) L.t = decode_tile<BN, PAIR>(p, item0, rank);
+    Cur P = L;
+#pragma unroll
+    for (int d = 0; d < kAhead; ++d) { fetch(L, qa[d], qb[d], qm[d]); advance(L); }
     int as = 0;
     uint32_t aph = 0;
     int cur_b = -1;
     float vmax = 0.f;
-    long long w_xe = 0, w_xp = 0;              // debug: cycles waiting for a free stage / preparing chunks
-    long long w_x1 = 0, w_x2 = 0, w_x3 = 0, w_x4 = 0;   // debug: rows, issue of the next chunk, proxy fence, arrive
-    if (Q > 0) issue(0);
+    long long w_xe = 0, w_xp = 0;              // debug: cycles waiting for a free stage / preparing rows
 #pragma unroll 1
-    for (int q = 0; q < Q; ++q) {
-      TileCoord t; int c;
-      chunk_of(q, t, c);
-      const bool main = c < p.nchunk_main;
-      const XfOperand& src = main ? xf.a : xf.x;
-      if (norm_a && c == 0 && t.b != cur_b) {
-        // the scale / shift table of this batch element is built by warp 3 (above): release the old one, wait for the new
-        named_bar_sync(2, kXfWarps * 32 + 32);
-        named_bar_sync(3, kXfWarps * 32 + 32);
-        cur_b = t.b;
-      }
-      const long long tc0 = p.dbg ? clock64() : 0;
-      ptx::mbar_wait(a_empty(as), aph ^ 1u);
-      const long long tc1 = p.dbg ? clock64() : 0;
-      if (src.s1 != nullptr) {
-        const uint32_t stage = sA(as);
-        const bool norm = main && norm_a;
-        const float* tsc = s_xsc + c * BK + j * 8;     // (only dereferenced when norm)
-        const float* tsh = s_xsh + c * BK + j * 8;
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-          int r; bool valid;
-          row_of(main, i, r, valid);
-          if (!valid) continue;
-          const int hy = r / HALO_W, hx = r - hy * HALO_W;
-          const int h = t.h0 - 1 + hy, w = t.w0 - 1 + hx;
-          uint2 h0 = make_uint2(0u, 0u), l0 = h0, h1 = h0, l1 = h0;
-          if (h >= 0 && h < p.H && w >= 0 && w < p.W) {          // zero padding of the ACTIVATED tensor outside the image
-            float4 a0 = v0[i], a1 = v1[i];
-            if (xf.dbg_mode & 2) {
-              h0 = make_uint2(__float_as_uint(a0.x), __float_as_uint(a0.y)); l0 = make_uint2(__float_as_uint(a0.z), __float_as_uint(a0.w));
-              h1 = make_uint2(__float_as_uint(a1.x), __float_as_uint(a1.y)); l1 = make_uint2(__float_as_uint(a1.z), __float_as_uint(a1.w));
-            } else {
-              if (norm) {
-                a0 = norm_act(a0, *reinterpret_cast<const float4*>(tsc), *reinterpret_cast<const float4*>(tsh), xf.silu);
-                a1 = norm_act(a1, *reinterpret_cast<const float4*>(tsc + 4), *reinterpret_cast<const float4*>(tsh + 4), xf.silu);
-              }
-              split4(a0, h0, l0); split4(a1, h1, l1);
-              vmax = amax4(a0, amax4(a1, vmax));
-            }
-          }
-          const uint32_t dst = stage + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
-          if (!(xf.dbg_mode & 4)) {
-            ptx::st_shared_v4(dst, pack8(h0, h1));
-            ptx::st_shared_v4(dst + A_PLANE_STRIDE, pack8(l0, l1));
-          } else if (h0.x == 0x12345678u && l1.y == 0x9abcdef0u) {
-            ptx::st_shared_v4(dst, pack8(h0, h1));               // keeps the math alive without storing
-          }
+    while (P.it < n_my_items) {
+      const bool main = P.c < p.nchunk_main;
+      const bool fused = chunk_fused(P.c);
+      if (P.i == 0) {
+        if (norm_a && P.c == 0 && P.t.b != cur_b) {
+          // the scale / shift table of this batch element is built by warp 3 (above): release the old one, wait for the new
+          named_bar_sync(2, kXfWarps * 32 + 32);
+          named_bar_sync(3, kXfWarps * 32 + 32);
+          cur_b = P.t.b;
         }
+        const long long tc0 = p.dbg ? clock64() : 0;
+        ptx::mbar_wait(a_empty(as), aph ^ 1u);
+        if (p.dbg) w_xe += clock64() - tc0;
       }
-      const long long tc2 = p.dbg ? clock64() : 0;
-      if (q + 1 < Q) issue(q + 1);             // v0 / v1 are free again: the next chunk's loads fly during the fence / arrive / wait
-      const long long tc3 = p.dbg ? clock64() : 0;
-      if (src.s1 != nullptr) ptx::fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
-      const long long tc4 = p.dbg ? clock64() : 0;
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(a_full(as));
-      if (++as == A_STAGES) { as = 0; aph ^= 1u; }
-      if (p.dbg) {
-        const long long tc5 = clock64();
-        w_xe += tc1 - tc0; w_xp += tc5 - tc1; w_x1 += tc2 - tc1; w_x2 += tc3 - tc2; w_x3 += tc4 - tc3; w_x4 += tc5 - tc4;
+      const long long tc1 = p.dbg ? clock64() : 0;
+      const int meta = qm[0];
+      if (meta & (1 << 16)) {
+        const int r = meta & 0xffff;
+        uint2 h0 = make_uint2(0u, 0u), l0 = h0, h1 = h0, l1 = h0;
+        if (meta & (1 << 17)) {                          // outside the image: zero padding of the ACTIVATED tensor
+          float4 a0 = qa[0], a1 = qb[0];
+          if (main && norm_a) {
+            const float* tsc = s_xsc + P.c * BK + j * 8;
+            const float* tsh = s_xsh + P.c * BK + j * 8;
+            a0 = norm_act(a0, *reinterpret_cast<const float4*>(tsc), *reinterpret_cast<const float4*>(tsh), xf.silu);
+            a1 = norm_act(a1, *reinterpret_cast<const float4*>(tsc + 4), *reinterpret_cast<const float4*>(tsh + 4), xf.silu);
+          }
+          split4(a0, h0, l0); split4(a1, h1, l1);
+          vmax = amax4(a0, amax4(a1, vmax));
+        }
+        const uint32_t dst = sA(as) + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
+        ptx::st_shared_v4(dst, pack8(h0, h1));
+        ptx::st_shared_v4(dst + A_PLANE_STRIDE, pack8(l0, l1));
       }
+      // rotate the rows in flight and request the next one
+#pragma unroll
+      for (int d = 0; d + 1 < kAhead; ++d) { qa[d] = qa[d + 1]; qb[d] = qb[d + 1]; qm[d] = qm[d + 1]; }
+      fetch(L, qa[kAhead - 1], qb[kAhead - 1], qm[kAhead - 1]);
+      advance(L);
+      if (P.i + 1 == rows_of(P.c)) {                     // last row of the chunk: hand the stage to the MMA warp
+        if (fused) ptx::fence_proxy_async();             // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(a_full(as));
+        if (++as == A_STAGES) { as = 0; aph ^= 1u; }
+      }
+      if (p.dbg) w_xp += clock64() - tc1;
+      advance(P);
     }
-    if (p.dbg && xt == 0) {
-      p.dbg[blockIdx.x * 16 + 6] = w_xe; p.dbg[blockIdx.x * 16 + 7] = w_xp; p.dbg[blockIdx.x * 16 + 8] = w_x1;
-      p.dbg[blockIdx.x * 16 + 9] = w_x2; p.dbg[blockIdx.x * 16 + 10] = w_x3; p.dbg[blockIdx.x * 16 + 11] = w_x4;
-    }
+    if (p.dbg && xt == 0) { p.dbg[blockIdx.x * 16 + 6] = w_xe; p.dbg[blockIdx.x * 16 + 7] = w_xp; }
     if (vmax > kHalfMax && xf.overflow) atomicAdd(xf.overflow, 1ull);
   } else if (is_epi) {
     // ------------------------------------------------------------------ epilogue (8 warps)
@@ -789,8 +776,6 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
     xf.x = XfOperand{a.fX.s1, a.fX.s2, a.fX.C1, a.fX.s2 ? a.fX.C2 : 0};
     xf.qs1 = a.fA.qs1; xf.qs2 = a.fA.qs2; xf.gamma = a.fA.gamma; xf.beta = a.fA.beta; xf.silu = a.fA.silu;
     xf.overflow = a.overflow;
-    static const int xf_dbg_mode = [] { const char* e = getenv("FLOWSE_XF_DBGMODE"); return e ? atoi(e) : 0; }();
-    xf.dbg_mode = xf_dbg_mode;
     auto bad = [&](const char* m) { if (err) *err = std::string("conv_halo (fused operand): ") + m; return 1; };
     if (a.fA.s1 && (xf.a.C1 + xf.a.C2 != a.Cin || xf.a.C1 % BK || a.Cin > kXfMaxC)) return bad("main operand channels");
     if (a.fA.s1 && a.fA.gamma && (!a.fA.beta || !a.fA.qs1 || (xf.a.C2 && !a.fA.qs2))) return bad("GroupNorm parameters / statistics missing");
@@ -838,9 +823,9 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
     }
     if (nl == 0) nl = 1;
     const double kb_per_cta = static_cast<double>(p.num_items) * (9.0 * p.nchunk_main + p.nchunk_sc) / nl;
-    fprintf(stderr, "[halo dbg%s] items=%d issuing ctas=%d kblocks/cta=%.0f (mma floor %.0f cyc) | issuer loop %.0f cyc: wait tmem %.0f, A %.0f, B %.0f | producer wait: A-free %.0f, B-free %.0f | transform: stage wait %.0f, prepare %.0f (rows %.0f, issue next %.0f, proxy fence %.0f, arrive %.0f)\n",
+    fprintf(stderr, "[halo dbg%s] items=%d issuing ctas=%d kblocks/cta=%.0f (mma floor %.0f cyc) | issuer loop %.0f cyc: wait tmem %.0f, A %.0f, B %.0f | producer wait: A-free %.0f, B-free %.0f | transform: stage wait %.0f, prepare %.0f\n",
             XF ? " XF" : "", p.num_items, nl, kb_per_cta, kb_per_cta * 768.0 * (BN / 128.0), sum[0] / nl, sum[1] / nl, sum[2] / nl, sum[3] / nl,
-            sum[4] / nctas, sum[5] / nctas, sum[6] / nctas, sum[7] / nctas, sum[8] / nctas, sum[9] / nctas, sum[10] / nctas, sum[11] / nctas);
+            sum[4] / nctas, sum[5] / nctas, sum[6] / nctas, sum[7] / nctas);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv_halo launch: ") + cudaGetErrorString(e); return 1; }
