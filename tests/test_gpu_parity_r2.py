@@ -325,36 +325,53 @@ def test_rk_lincomb_kernel_vs_numpy(ctx):
 
 
 def test_black_box_rk45_vs_scipy_oracle(synthetic_sd):
-    """get_black_box_solver (RK45 on the device) against scipy's solve_ivp driving the CPU oracle's vector field - the
-    reference's own construction (sampling/__init__.py:64-114) - on a [1,1,256,64] spectrogram: same number of function
-    evaluations (every accept / reject decision agrees) and the same sample within the north-star tolerance."""
+    """get_black_box_solver (RK45 on the device) against scipy's solve_ivp - the reference's own construction
+    (sampling/__init__.py:64-114).  An adaptive solve is discontinuous in its accept / reject decisions: moving x0 by one
+    fp32 ulp changes 98 % of the output bins of this very case beyond the tolerance (recorded below), so the SOLVER is
+    pinned with one and the same vector field on both sides (the oracle evaluated by torch on the GPU, fp32): the device
+    integrator must then reproduce scipy bit for bit - same evaluations, same accepted steps, same sample.  The vector
+    field itself is pinned by the forward / sampler parity tests."""
     from scipy import integrate
     from flowmse_b200.model import VFModel
     from flowmse_b200.sampling import get_black_box_solver
+    from flowmse_b200.sampling import _rk45_on_device
     rtol = atol = 1e-3
+    Y = _rand_c((1, 1, 256, 64), 111, 0.3)
+    z = _rand_c((1, 1, 256, 64), 112, np.sqrt(0.5))
+    x0 = orc.prior_sample(Y, z)
+    sd_cuda = {k: v.cuda() for k, v in synthetic_sd.items()}
+    Yc = Y.cuda()
+
+    def vf_oracle_cuda(x, t, y):
+        with torch.device("cuda"):
+            return orc.vf_forward(sd_cuda, x, t, y)
+
+    def ode_func(t, flat):           # what the reference's ode_func does: host <-> device round trip per evaluation
+        xt = torch.from_numpy(flat.reshape(tuple(Y.shape))).type(torch.complex64).cuda()
+        return vf_oracle_cuda(xt, torch.ones(1, device="cuda") * t, Yc).cpu().numpy().reshape(-1)
+
+    with _fp32_torch_cuda():
+        state, nfe = _rk45_on_device(vf_oracle_cuda, x0.cuda(), Yc, 1.0, 0.03, rtol, atol)
+        sol = integrate.solve_ivp(ode_func, (1.0, 0.03), x0.numpy().reshape(-1), rtol=rtol, atol=atol, method="RK45")
+        x1 = torch.view_as_complex(torch.nextafter(torch.view_as_real(x0), torch.full((), float("inf"))))
+        sol_ulp = integrate.solve_ivp(ode_func, (1.0, 0.03), x1.numpy().reshape(-1), rtol=rtol, atol=atol, method="RK45")
+    x_dev = state.reshape(Y.shape).type(torch.complex64)
+    x_ref = torch.tensor(sol.y[:, -1]).reshape(Y.shape).type(torch.complex64)
+    frac, mx = _sep(x_dev, x_ref)
+    f_ulp, m_ulp = _sep(torch.tensor(sol_ulp.y[:, -1]).reshape(Y.shape).type(torch.complex64), x_ref)
+    _record("black_box_rk45_T64", dict(rtol=rtol, atol=atol, nfe_device=nfe, nfe_scipy=int(sol.nfev), frac_outside=frac, max_abs=mx,
+                                       scipy_vs_scipy_x0_plus_1ulp=dict(frac_outside=f_ulp, max_abs=m_ulp, nfe=int(sol_ulp.nfev))))
+    assert nfe == sol.nfev, (nfe, sol.nfev)
+    assert mx <= 1e-6, (frac, mx)
+    # through the public entry point with the B200 vector field: runs, counts its evaluations, stays finite; any other
+    # scipy method takes the reference's host route
     model = VFModel(backbone="ncsnpp", ode="flowmatching")
     model.dnn.load_state_dict(synthetic_sd, strict=True)
     model.eval()
-    Y = _rand_c((1, 1, 256, 64), 111, 0.3)
     torch.manual_seed(4321)
-    x, nfe = get_black_box_solver(model.ode, model, Y.cuda(), rtol=rtol, atol=atol, T_rev=1.0, t_eps=0.03)()
+    x, n1 = get_black_box_solver(model.ode, model, Yc, rtol=rtol, atol=atol, T_rev=1.0, t_eps=0.03)()
+    assert x.shape == Y.shape and x.dtype == torch.complex64 and n1 >= 8 and (n1 - 2) % 6 == 0
+    assert torch.isfinite(torch.view_as_real(x)).all()
     torch.manual_seed(4321)
-    z = torch.randn_like(Y.cuda()).cpu()                      # the prior draw the solver made
-    x0 = orc.prior_sample(Y, z)
-    torch.set_num_threads(os.cpu_count() or 1)
-
-    def ode_func(t, flat):
-        xt = torch.from_numpy(flat.reshape(tuple(Y.shape))).type(torch.complex64)
-        with torch.no_grad():
-            return orc.vf_forward(synthetic_sd, xt, torch.ones(1) * t, Y).numpy().reshape(-1)
-
-    sol = integrate.solve_ivp(ode_func, (1.0, 0.03), x0.numpy().reshape(-1), rtol=rtol, atol=atol, method="RK45")
-    x_ref = torch.tensor(sol.y[:, -1]).reshape(Y.shape).type(torch.complex64)
-    frac, mx = _sep(x, x_ref)
-    _record("black_box_rk45_T64", dict(rtol=rtol, atol=atol, nfe_device=nfe, nfe_scipy=int(sol.nfev), frac_outside=frac, max_abs=mx))
-    assert nfe == sol.nfev, (nfe, sol.nfev)
-    assert frac <= 1e-4 and mx < 1e-3, (frac, mx)
-    # any other scipy method takes the reference's host route and still works with the B200 vector field
-    torch.manual_seed(4321)
-    x2, nfe2 = get_black_box_solver(model.ode, model, Y.cuda(), rtol=1e-2, atol=1e-2, method="RK23")()
-    assert x2.shape == Y.shape and nfe2 > 0 and torch.isfinite(torch.view_as_real(x2)).all()
+    x2, n2 = get_black_box_solver(model.ode, model, Yc, rtol=1e-2, atol=1e-2, method="RK23")()
+    assert x2.shape == Y.shape and n2 > 0 and torch.isfinite(torch.view_as_real(x2)).all()
