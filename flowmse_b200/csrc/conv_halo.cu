@@ -184,7 +184,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int BN, int NMAIN, bool PAIR, bool XF>
+template <int BN, int NMAIN, bool PAIR, bool XF, int AHEAD = 6>
 __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX,
                  const __grid_constant__ CUtensorMap tmW, const HaloParams p, const XfParams xf) {
@@ -488,7 +488,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           base + (static_cast<size_t>(k.t.b) * p.H * p.W + static_cast<size_t>(h) * p.W + w) * ld + j * 8);
       a0 = __ldg(g); a1 = __ldg(g + 1);
     };
-    constexpr int kAhead = 3;                  // rows in flight per thread (24 KB per SM)
+    constexpr int kAhead = AHEAD;              // rows in flight per thread (6 rows = 48 KB per SM: a whole chunk)
     float4 qa[kAhead], qb[kAhead];
     int qm[kAhead];
     Cur L{0, 0, 0, TileCoord{0, 0, 0, 0}};
@@ -747,12 +747,12 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int NMAIN, bool PAIR, bool XF = false>
+template <int BN, int NMAIN, bool PAIR, bool XF = false, int AHEAD = 6>
 int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   using C = HCfg<BN, NMAIN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, NMAIN, PAIR, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, NMAIN, PAIR, XF, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(halo): ") + cudaGetErrorString(e); return 1; }
     attr_set = true;
@@ -809,7 +809,7 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   long long* dbuf = nullptr;
   const size_t nctas = cfg.gridDim.x;
   if (dbg) { cudaMalloc(&dbuf, nctas * 16 * sizeof(long long)); cudaMemset(dbuf, 0, nctas * 16 * sizeof(long long)); p.dbg = dbuf; }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, NMAIN, PAIR, XF>, tmA, tmX, tmW, p, xf);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, NMAIN, PAIR, XF, AHEAD>, tmA, tmX, tmW, p, xf);
   ++launch_counter();
   if (dbg) {
     cudaStreamSynchronize(s);
@@ -845,7 +845,8 @@ int launch_conv_halo(const ConvGemmArgs& a, int variant, cudaStream_t s, std::st
   if (!conv_halo_supported(a)) { if (err) *err = "conv_halo: unsupported shape"; return 1; }
   if (a.fA.s1 || a.fX.s1) {
     if (a.Npad % 128 != 0) { if (err) *err = "conv_halo: fused operands need Cout tiles of 128"; return 1; }
-    return launch_halo<128, 1, false, true>(a, s, err);
+    static const int ahead = [] { const char* e = getenv("FLOWSE_XF_AHEAD"); return e ? atoi(e) : 6; }();   // measurement switch
+    return ahead == 3 ? launch_halo<128, 1, false, true, 3>(a, s, err) : launch_halo<128, 1, false, true, 6>(a, s, err);
   }
   if (a.Npad % 128 == 0) {
     const int m_tiles = a.B * (a.W / TW) * (a.H / TH);
