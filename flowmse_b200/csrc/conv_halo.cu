@@ -184,7 +184,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int BN, int NMAIN, bool PAIR, bool XF, int AHEAD = 6>
+template <int BN, int NMAIN, bool PAIR, bool XF>
 __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX,
                  const __grid_constant__ CUtensorMap tmW, const HaloParams p, const XfParams xf) {
@@ -444,68 +444,70 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (is_xf) {
     // ------------------------------------------------------------------ operand transform (warps 12..19, XF only)
     // A thread owns one 16-byte column (8 channels) of every 32nd operand row: 6 rows of a 3x3 chunk (180 halo rows), 4 of
-    // a 1x1 shortcut chunk (its 128 centre rows).  The rows of all chunks of all tiles form ONE stream that is walked by
-    // a ROLLED loop - one row per trip, ~150 instructions - with the global loads running kAhead rows in front of the row
-    // being normalised / split / stored (values rotate through registers).  Keeping this loop small matters as much as
-    // the prefetch: an unrolled version of the same work made the kernel 80 KB of SASS, and the transform warps then ran
-    // at a tenth of their issue rate on instruction-cache misses (profiles/README.md, round 2).
+    // a 1x1 shortcut chunk (its 128 centre rows).  Work unit = a BATCH of 3 row slots (two batches per chunk), prepared as
+    // straight-line code so that the three rows' dependency chains (FFMA -> EX2 -> RCP -> pack -> unpack -> pack) overlap:
+    // with only two transform warps per scheduler there is no other latency hiding.  (Measured alternatives, all slower:
+    // one rolled row per trip - 12 % of the cycles issuing, the rest dependency stalls; six rows unrolled with every
+    // variant inlined - 80 KB of SASS, instruction-cache bound.)  The loads of the next batch are issued as soon as a
+    // batch's registers are free, before the wait for the next operand stage.
     const int xt = static_cast<int>(threadIdx.x) - w_xf0 * 32;            // 0..255
     const int j = xt & 7;                      // 16-byte column of the 128-byte operand row: channels 8j .. 8j+7 of the chunk
     const int r0 = xt >> 3;                    // rows r0 + 32 i
     const bool norm_a = xf.a.s1 != nullptr && xf.gamma != nullptr;
     const int n_my_items = item0 < p.num_items ? (p.num_items - item0 + item_stride - 1) / item_stride : 0;
-    // position in the row stream: work item ordinal, chunk, row slot (+ the tile of that item)
-    struct Cur { int it, c, i; TileCoord t; };
+    struct Cur { int it, c, hb; TileCoord t; };               // work item ordinal, chunk, batch (0 / 1) + the item's tile
     auto chunk_fused = [&](int c) { return (c < p.nchunk_main ? xf.a.s1 : xf.x.s1) != nullptr; };
-    auto rows_of = [&](int c) { return !chunk_fused(c) ? 1 : (c < p.nchunk_main ? 6 : 4); };   // TMA-fed chunk: one empty slot
     auto advance = [&](Cur& k) {
-      if (++k.i == rows_of(k.c)) {
-        k.i = 0;
+      if (++k.hb == 2) {
+        k.hb = 0;
         if (++k.c == nchunks) {
           k.c = 0;
           if (++k.it < n_my_items) k.t = decode_tile<BN, PAIR>(p, item0 + k.it * item_stride, rank);
         }
       }
     };
-    // meta: bits 0..15 operand row, bit 16 row exists, bit 17 pixel inside the image
-    auto fetch = [&](const Cur& k, float4& a0, float4& a1, int& meta) {
-      a0 = make_float4(0.f, 0.f, 0.f, 0.f); a1 = a0; meta = 0;
-      if (k.it >= n_my_items || !chunk_fused(k.c)) return;
+    constexpr int NB = 3;                      // row slots per batch
+    float4 v0[NB], v1[NB];
+    int meta[NB];                              // bits 0..15 operand row, bit 16 row exists, bit 17 pixel inside the image
+    auto fetch = [&](const Cur& k) {
+      const bool live = k.it < n_my_items && chunk_fused(k.c);
       const bool main = k.c < p.nchunk_main;
       const XfOperand& src = main ? xf.a : xf.x;
-      const int slot = r0 + 32 * k.i;
-      const int r = main ? slot : ((slot >> 3) + 1) * HALO_W + (slot & 7) + 1;
-      if (r >= A_ROWS) return;
-      const int hy = r / HALO_W, hx = r - hy * HALO_W;
-      const int h = k.t.h0 - 1 + hy, w = k.t.w0 - 1 + hx;
-      const bool inb = h >= 0 && h < p.H && w >= 0 && w < p.W;
-      meta = r | (1 << 16) | (inb ? (1 << 17) : 0);
-      if (!inb) return;
       const int cg = (main ? k.c : k.c - p.nchunk_main) * BK;
-      const float* base; int ld;
-      if (cg < src.C1) { base = src.s1 + cg; ld = src.C1; } else { base = src.s2 + (cg - src.C1); ld = src.C2; }
-      const float4* g = reinterpret_cast<const float4*>(
-          base + (static_cast<size_t>(k.t.b) * p.H * p.W + static_cast<size_t>(h) * p.W + w) * ld + j * 8);
-      a0 = __ldg(g); a1 = __ldg(g + 1);
-    };
-    constexpr int kAhead = AHEAD;              // rows in flight per thread (6 rows = 48 KB per SM: a whole chunk)
-    float4 qa[kAhead], qb[kAhead];
-    int qm[kAhead];
-    Cur L{0, 0, 0, TileCoord{0, 0, 0, 0}};
-    if (n_my_items > 0) L.t = decode_tile<BN, PAIR>(p, item0, rank);
-    Cur P = L;
+      const float* base = nullptr; int ld = 0;
+      if (live) {
+        if (cg < src.C1) { base = src.s1 + cg; ld = src.C1; } else { base = src.s2 + (cg - src.C1); ld = src.C2; }
+        base += static_cast<size_t>(k.t.b) * p.H * p.W * ld + j * 8;
+      }
 #pragma unroll
-    for (int d = 0; d < kAhead; ++d) { fetch(L, qa[d], qb[d], qm[d]); advance(L); }
+      for (int i = 0; i < NB; ++i) {
+        const int slot = r0 + 32 * (NB * k.hb + i);            // 0..191
+        const int r = main ? slot : ((slot >> 3) + 1) * HALO_W + (slot & 7) + 1;
+        const bool exists = live && (main ? slot < A_ROWS : slot < BM);
+        const int hy = r / HALO_W, hx = r - hy * HALO_W;
+        const int h = k.t.h0 - 1 + hy, w = k.t.w0 - 1 + hx;
+        const bool inb = exists && h >= 0 && h < p.H && w >= 0 && w < p.W;
+        meta[i] = r | (exists ? (1 << 16) : 0) | (inb ? (1 << 17) : 0);
+        v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i];
+        if (inb) {
+          const float4* g = reinterpret_cast<const float4*>(base + (static_cast<size_t>(h) * p.W + w) * ld);
+          v0[i] = __ldg(g); v1[i] = __ldg(g + 1);
+        }
+      }
+    };
+    Cur P{0, 0, 0, TileCoord{0, 0, 0, 0}};
+    if (n_my_items > 0) P.t = decode_tile<BN, PAIR>(p, item0, rank);
+    fetch(P);
     int as = 0;
     uint32_t aph = 0;
     int cur_b = -1;
     float vmax = 0.f;
-    long long w_xe = 0, w_xp = 0;              // debug: cycles waiting for a free stage / preparing rows
+    long long w_xe = 0, w_xp = 0;              // debug: cycles waiting for a free stage / preparing batches
 #pragma unroll 1
     while (P.it < n_my_items) {
       const bool main = P.c < p.nchunk_main;
       const bool fused = chunk_fused(P.c);
-      if (P.i == 0) {
+      if (P.hb == 0) {
         if (norm_a && P.c == 0 && P.t.b != cur_b) {
           // the scale / shift table of this batch element is built by warp 3 (above): release the old one, wait for the new
           named_bar_sync(2, kXfWarps * 32 + 32);
@@ -517,38 +519,45 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.dbg) w_xe += clock64() - tc0;
       }
       const long long tc1 = p.dbg ? clock64() : 0;
-      const int meta = qm[0];
-      if (meta & (1 << 16)) {
-        const int r = meta & 0xffff;
-        uint2 h0 = make_uint2(0u, 0u), l0 = h0, h1 = h0, l1 = h0;
-        if (meta & (1 << 17)) {                          // outside the image: zero padding of the ACTIVATED tensor
-          float4 a0 = qa[0], a1 = qb[0];
-          if (main && norm_a) {
-            const float* tsc = s_xsc + P.c * BK + j * 8;
-            const float* tsh = s_xsh + P.c * BK + j * 8;
-            a0 = norm_act(a0, *reinterpret_cast<const float4*>(tsc), *reinterpret_cast<const float4*>(tsh), xf.silu);
-            a1 = norm_act(a1, *reinterpret_cast<const float4*>(tsc + 4), *reinterpret_cast<const float4*>(tsh + 4), xf.silu);
-          }
+      if (fused) {
+        const bool norm = main && norm_a;
+        float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
+        if (norm) {
+          const float* tsc = s_xsc + P.c * BK + j * 8;
+          const float* tsh = s_xsh + P.c * BK + j * 8;
+          sc0 = *reinterpret_cast<const float4*>(tsc); sc1 = *reinterpret_cast<const float4*>(tsc + 4);
+          sh0 = *reinterpret_cast<const float4*>(tsh); sh1 = *reinterpret_cast<const float4*>(tsh + 4);
+        }
+        const int silu = norm ? xf.silu : 0;
+        const uint32_t stage = sA(as);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          // rows outside the image hold zeros (zero padding of the ACTIVATED tensor); the affine of a shortcut chunk is 1, 0
+          float4 a0 = v0[i], a1 = v1[i];
+          if (norm) { a0 = norm_act(a0, sc0, sh0, silu); a1 = norm_act(a1, sc1, sh1, silu); }
+          const bool inb = (meta[i] >> 17) & 1;
+          if (!inb) { a0 = make_float4(0.f, 0.f, 0.f, 0.f); a1 = a0; }
+          uint2 h0, l0, h1, l1;
           split4(a0, h0, l0); split4(a1, h1, l1);
           vmax = amax4(a0, amax4(a1, vmax));
+          if ((meta[i] >> 16) & 1) {
+            const int r = meta[i] & 0xffff;
+            const uint32_t dst = stage + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
+            ptx::st_shared_v4(dst, pack8(h0, h1));
+            ptx::st_shared_v4(dst + A_PLANE_STRIDE, pack8(l0, l1));
+          }
         }
-        const uint32_t dst = sA(as) + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
-        ptx::st_shared_v4(dst, pack8(h0, h1));
-        ptx::st_shared_v4(dst + A_PLANE_STRIDE, pack8(l0, l1));
       }
-      // rotate the rows in flight and request the next one
-#pragma unroll
-      for (int d = 0; d + 1 < kAhead; ++d) { qa[d] = qa[d + 1]; qb[d] = qb[d + 1]; qm[d] = qm[d + 1]; }
-      fetch(L, qa[kAhead - 1], qb[kAhead - 1], qm[kAhead - 1]);
-      advance(L);
-      if (P.i + 1 == rows_of(P.c)) {                     // last row of the chunk: hand the stage to the MMA warp
-        if (fused) ptx::fence_proxy_async();             // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      const bool last = P.hb == 1;
+      advance(P);
+      fetch(P);                                // the registers are free again: the next batch's loads fly during the hand-over
+      if (last) {                              // second batch of the chunk done: hand the stage to the MMA warp
+        if (fused) ptx::fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(a_full(as));
         if (++as == A_STAGES) { as = 0; aph ^= 1u; }
       }
       if (p.dbg) w_xp += clock64() - tc1;
-      advance(P);
     }
     if (p.dbg && xt == 0) { p.dbg[blockIdx.x * 16 + 6] = w_xe; p.dbg[blockIdx.x * 16 + 7] = w_xp; }
     if (vmax > kHalfMax && xf.overflow) atomicAdd(xf.overflow, 1ull);
@@ -747,12 +756,12 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int NMAIN, bool PAIR, bool XF = false, int AHEAD = 6>
+template <int BN, int NMAIN, bool PAIR, bool XF = false>
 int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   using C = HCfg<BN, NMAIN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, NMAIN, PAIR, XF, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, NMAIN, PAIR, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(halo): ") + cudaGetErrorString(e); return 1; }
     attr_set = true;
@@ -809,7 +818,7 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   long long* dbuf = nullptr;
   const size_t nctas = cfg.gridDim.x;
   if (dbg) { cudaMalloc(&dbuf, nctas * 16 * sizeof(long long)); cudaMemset(dbuf, 0, nctas * 16 * sizeof(long long)); p.dbg = dbuf; }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, NMAIN, PAIR, XF, AHEAD>, tmA, tmX, tmW, p, xf);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, NMAIN, PAIR, XF>, tmA, tmX, tmW, p, xf);
   ++launch_counter();
   if (dbg) {
     cudaStreamSynchronize(s);
@@ -845,8 +854,7 @@ int launch_conv_halo(const ConvGemmArgs& a, int variant, cudaStream_t s, std::st
   if (!conv_halo_supported(a)) { if (err) *err = "conv_halo: unsupported shape"; return 1; }
   if (a.fA.s1 || a.fX.s1) {
     if (a.Npad % 128 != 0) { if (err) *err = "conv_halo: fused operands need Cout tiles of 128"; return 1; }
-    static const int ahead = [] { const char* e = getenv("FLOWSE_XF_AHEAD"); return e ? atoi(e) : 6; }();   // measurement switch
-    return ahead == 3 ? launch_halo<128, 1, false, true, 3>(a, s, err) : launch_halo<128, 1, false, true, 6>(a, s, err);
+    return launch_halo<128, 1, false, true>(a, s, err);
   }
   if (a.Npad % 128 == 0) {
     const int m_tiles = a.B * (a.W / TW) * (a.H / TH);

@@ -201,7 +201,7 @@ struct flowse_ctx {
   unsigned long long* overflow = nullptr;
   double* rk_acc = nullptr;                 // device accumulator of flowse_rk_lincomb's error norm
   int whole_graph = 1;                      // capture the whole sampler call as one CUDA graph (second call with the same schedule)
-  int fuse_prep = 2;                        // conv kernels prepare their own operands (no standalone prep pass): 1 halo layers, 2 all
+  int fuse_prep = 1;                        // conv kernels prepare their own operands (no standalone prep pass): 1 halo layers, 2 all
 };
 
 namespace {
