@@ -66,6 +66,9 @@ constexpr int kXfWarps = 8;                              // transform warps of t
 constexpr int kFirstXfWarp = kFirstEpiWarp + kEpiWarps;  // warps 12..19
 constexpr int NUM_THREADS_XF = (kFirstXfWarp + kXfWarps) * 32;   // 640
 constexpr int kXfMaxC = 512;                             // channels of a fused operand (scale / shift table in smem)
+#ifndef XF_NB
+#define XF_NB 3
+#endif
 
 template <int BN, int NMAIN, bool PAIR>
 struct HCfg {
@@ -455,10 +458,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int r0 = xt >> 3;                    // rows r0 + 32 i
     const bool norm_a = xf.a.s1 != nullptr && xf.gamma != nullptr;
     const int n_my_items = item0 < p.num_items ? (p.num_items - item0 + item_stride - 1) / item_stride : 0;
-    struct Cur { int it, c, hb; TileCoord t; };               // work item ordinal, chunk, batch (0 / 1) + the item's tile
+    constexpr int NB = XF_NB;                  // row slots per batch
+    constexpr int HB = 6 / NB;                 // batches per chunk
+    struct Cur { int it, c, hb; TileCoord t; };               // work item ordinal, chunk, batch + the item's tile
     auto chunk_fused = [&](int c) { return (c < p.nchunk_main ? xf.a.s1 : xf.x.s1) != nullptr; };
     auto advance = [&](Cur& k) {
-      if (++k.hb == 2) {
+      if (++k.hb == HB) {
         k.hb = 0;
         if (++k.c == nchunks) {
           k.c = 0;
@@ -466,7 +471,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     };
-    constexpr int NB = 3;                      // row slots per batch
     float4 v0[NB], v1[NB];
     int meta[NB];                              // bits 0..15 operand row, bit 16 row exists, bit 17 pixel inside the image
     auto fetch = [&](const Cur& k) {
@@ -548,7 +552,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      const bool last = P.hb == 1;
+      const bool last = P.hb == HB - 1;
       advance(P);
       fetch(P);                                // the registers are free again: the next batch's loads fly during the hand-over
       if (last) {                              // second batch of the chunk done: hand the stage to the MMA warp

@@ -13,7 +13,7 @@ import torch
 from . import ncsnpp_spec as spec
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflowse.so")
+LIB_PATH = os.environ.get("FLOWSE_LIB") or os.path.join(_HERE, "libflowse.so")   # FLOWSE_LIB: A/B builds of the library
 _lib = None
 
 

@@ -284,3 +284,47 @@ def test_load_reference_style_checkpoint_with_pickled_data_module_cls(tmp_path, 
     model.eval(no_ema=True)
     assert torch.equal(model.dnn.state_dict()[name], synthetic_sd[name])
     assert model.ode.sigma_max == hp.get("sigma_max", 0.487) and model.t_eps == hp.get("t_eps", 0.03)
+
+
+def test_rk45_restatement_matches_scipy_on_cpu(monkeypatch):
+    """The Dormand-Prince tableau, initial-step selection and step-size controller of sampling._rk45_on_device against
+    scipy.integrate.solve_ivp(method="RK45") - the solver the reference's get_black_box_solver calls
+    (sampling/__init__.py:64-114) - on a small complex system.  The libflowse kernel behind Context.rk_lincomb is replaced
+    by its torch definition here (no GPU); the GPU test checks the kernel itself and the device run."""
+    import numpy as np
+    from scipy import integrate
+    import flowmse_b200.runtime as rt
+    import flowmse_b200.sampling as S
+
+    class TorchLincomb:
+        def rk_lincomb(self, base64, K32, coef, out64=None, out32=None, norm_of=None, rtol=0.0, atol=0.0):
+            v = torch.zeros_like(K32[0], dtype=torch.complex128) if base64 is None else base64.clone()
+            for s, c in enumerate(coef):
+                v = v + c * K32[s].to(torch.complex128)
+            if out64 is not None:
+                out64.copy_(v)
+            if out32 is not None:
+                out32.copy_(v.to(torch.complex64))
+            if norm_of is not None:
+                scale = atol + rtol * torch.maximum(norm_of[0].abs(), norm_of[1].abs())
+                return float(((v.abs() / scale) ** 2).sum())
+
+    monkeypatch.setattr(rt, "get_context", lambda dev: TorchLincomb())
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(16, 16, generator=g) * 0.8
+    y = torch.view_as_complex(torch.randn(1, 1, 4, 4, 2, generator=g))
+    x0 = torch.view_as_complex(torch.randn(1, 1, 4, 4, 2, generator=g))
+
+    def VF(x, t, yy):          # stiff towards t -> 0 like the network's 1/t output scale
+        v = (x.reshape(-1).real @ A.T) + 1j * (x.reshape(-1).imag @ A.T)
+        return (-(v.reshape(x.shape)) * (0.2 / t.reshape(-1, 1, 1, 1)) + 0.1 * yy).to(torch.complex64)
+
+    def ode_func(t, flat):
+        xt = torch.from_numpy(flat.reshape(tuple(y.shape))).type(torch.complex64)
+        return VF(xt, torch.ones(1) * t, y).numpy().reshape(-1)
+
+    for tol in (1e-3, 1e-6):
+        state, nfe = S._rk45_on_device(VF, x0, y, 1.0, 0.03, tol, tol)
+        sol = integrate.solve_ivp(ode_func, (1.0, 0.03), x0.numpy().reshape(-1), rtol=tol, atol=tol, method="RK45")
+        assert nfe == sol.nfev
+        assert np.abs(state.numpy().reshape(-1) - sol.y[:, -1]).max() < 1e-6   # coefficient products differ in the last fp64 bit
