@@ -67,7 +67,7 @@ constexpr int kFirstXfWarp = kFirstEpiWarp + kEpiWarps;  // warps 12..19
 constexpr int NUM_THREADS_XF = (kFirstXfWarp + kXfWarps) * 32;   // 640
 constexpr int kXfMaxC = 512;                             // channels of a fused operand (scale / shift table in smem)
 #ifndef XF_NB
-#define XF_NB 3
+#define XF_NB 6
 #endif
 
 template <int BN, int NMAIN, bool PAIR>
