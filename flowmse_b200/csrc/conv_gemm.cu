@@ -18,14 +18,8 @@
 //  * The ResBlock's 1x1 shortcut conv (Conv_2) is folded into the second 3x3 conv as extra K blocks read from a
 //    second tensor map, so (x_shortcut + h)/sqrt(2) costs no extra pass.
 //  * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
-//    warps 2..9 = epilogue (TMEM -> registers -> bias/residual/scale -> global).
-//  * XF variant (fused operand preparation, see conv_halo.cu): during the main loop the epilogue warps have nothing to do,
-//    so they build the A operand of every K block themselves - fp32 NHWC activations -> GroupNorm + SiLU -> fp16 hi/lo ->
-//    swizzled shared-memory rows - and the standalone prep launch in front of every low-resolution conv disappears (these
-//    layers are a chain of ~120 short dependent launches per evaluation).  The tap-shifted tile is re-transformed for each
-//    of its 9 taps; at <= 32 x 64 pixels that redundancy costs less than a launch.
+//    warps 2..5 = epilogue (TMEM -> registers -> bias/residual/scale -> global).
 #include "flowse_internal.h"
-#include "operand.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -95,18 +89,6 @@ struct GemmParams {
   int cluster_s;
 };
 
-// fused operand sources (XF variant), device view of FusedOperand
-struct XfOperand { const float* s1; const float* s2; int C1, C2; };
-struct XfParams {
-  XfOperand a, x;                        // main / shortcut operand; s1 == nullptr: that operand comes through TMA
-  const double* qs1; const double* qs2;  // quad statistics of a.s1 / a.s2
-  const float* gamma; const float* beta; // GroupNorm affine of the main operand (over C1 + C2 channels)
-  int silu;
-  int tw_shift;                          // log2(TW): tile row r -> (r >> tw_shift, r & (TW - 1))
-  unsigned long long* overflow;
-};
-constexpr int kXfMaxC = 512;
-
 struct CtaTile { int b, h0, w0, n0; };
 
 // Split-K cluster reduction of one thread: CTA z of an S-CTA cluster owns rows [z*128/S, (z+1)*128/S) of the tile; warp rg
@@ -158,15 +140,14 @@ __device__ __forceinline__ void cluster_reduce_rows(const GemmParams& p, const C
   }
 }
 
-template <int BN, bool XF>
+template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX,
-                         const __grid_constant__ CUtensorMap tmW, const GemmParams p, const XfParams xf) {
+                         const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * C::STAGES + 1];     // full[STAGES], empty[STAGES], tmem_full
   __shared__ uint32_t tmem_slot_var;
-  __shared__ __align__(16) float s_xsc[XF ? kXfMaxC : 4], s_xsh[XF ? kXfMaxC : 4];   // GroupNorm scale / shift per channel
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = ptx::smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -202,7 +183,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     ptx::prefetch_tensormap(&tmX);
     ptx::prefetch_tensormap(&tmW);
     for (int s = 0; s < C::STAGES; ++s) {
-      ptx::mbar_init(full_bar(s), XF ? 1 + kEpiWarps : 1);     // XF: the producer and every transform (= epilogue) warp arrive
+      ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);
     }
     ptx::mbar_init(tmem_full_bar, 1);
@@ -230,11 +211,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const uint32_t sA_lo = sA_hi + A_BYTES;
         const uint32_t sB_hi = sA_lo + A_BYTES;
         const uint32_t sB_lo = sB_hi + C::B_BYTES;
-        const bool main = kb < nkb_main;
-        const bool a_fused = XF && (main ? xf.a.s1 : xf.x.s1) != nullptr;      // the transform warps fill the A tile
-        ptx::mbar_expect_tx(full_bar(stage), a_fused ? 2 * C::B_BYTES : C::STAGE_BYTES);
-        if (a_fused) {
-        } else if (main) {
+        ptx::mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+        if (kb < nkb_main) {
           const int tap = kb / p.nchunk_main;
           const int ch = kb - tap * p.nchunk_main;
           int dy = 0, dx = 0;
@@ -252,48 +230,6 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (XF && xf.a.s1 != nullptr && xf.gamma != nullptr) {
-      // GroupNorm scale / shift table of this CTA's batch element (same arithmetic as the standalone prep, kernels_gn.cu),
-      // built by the MMA warp while the transform warps' first activation loads are in flight
-      const int Ca = xf.a.C1 + xf.a.C2;
-      const int cpg = Ca / kGroups;
-      float ga[kXfMaxC / 32], be[kXfMaxC / 32];         // requested before the statistics: one global round trip in all
-#pragma unroll
-      for (int i = 0; i < kXfMaxC / 32; ++i) {
-        const int c = lane + 32 * i;
-        ga[i] = c < Ca ? __ldg(xf.gamma + c) : 0.f; be[i] = c < Ca ? __ldg(xf.beta + c) : 0.f;
-      }
-      double su = 0.0, sq = 0.0;                        // lane = group
-      const int qpg = cpg >> 2, q1 = xf.a.C1 >> 2;
-      for (int jj = 0; jj < qpg; ++jj) {
-        const int qd = lane * qpg + jj;
-#pragma unroll
-        for (int r = 0; r < kStatReplicas; ++r) {
-          const double2 v = (qd < q1)
-              ? reinterpret_cast<const double2*>(qstat_slot(xf.qs1, b, r, q1))[qd]
-              : reinterpret_cast<const double2*>(qstat_slot(xf.qs2, b, r, xf.a.C2 >> 2))[qd - q1];
-          su += v.x; sq += v.y;
-        }
-      }
-      const double n = static_cast<double>(p.H) * p.W * cpg;
-      const double mean_d = su / n;
-      double var = sq / n - mean_d * mean_d;
-      if (var < 0.0) var = 0.0;
-      const float mean = static_cast<float>(mean_d);
-      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
-#pragma unroll
-      for (int i = 0; i < kXfMaxC / 32; ++i) {
-        const int c = lane + 32 * i;
-        const int g = (c < Ca ? c : 0) / cpg;
-        const float m = __shfl_sync(0xffffffffu, mean, g), rs = __shfl_sync(0xffffffffu, rstd, g);
-        if (c < Ca) {
-          const float sc = rs * ga[i];
-          s_xsc[c] = sc;
-          s_xsh[c] = fmaf(-m, sc, be[i]);
-        }
-      }
-      asm volatile("bar.sync 2, 288;" ::: "memory");    // table complete: transform warps (256 threads) + this warp
-    }
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(BM, BN);
@@ -371,93 +307,6 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     };
     if (active) load_res(0);
     const float post = p.div_sqrt2 ? 0.70710678118654752440f : 1.0f;
-
-    if constexpr (XF) {
-      // -------------------------------------------------------------- operand transform (the epilogue warps, XF only)
-      // K block kb = (tap, 64-channel chunk): 128 tile rows x 8 sixteen-byte columns = 4 rows per thread.  All rows of
-      // all K blocks of this CTA form one stream walked by a ROLLED loop (one row per trip) with the global loads kAhead
-      // rows in front of the row being prepared - same scheme and same reason (instruction-cache footprint) as in
-      // conv_halo.cu.
-      const int xt = static_cast<int>(threadIdx.x) - 64;     // 0..255
-      const int j = xt & 7, rr0 = xt >> 3;
-      const bool norm_a = xf.a.s1 != nullptr && xf.gamma != nullptr;
-      auto kb_fused = [&](int kb) { return (kb < nkb_main ? xf.a.s1 : xf.x.s1) != nullptr; };
-      auto rows_of = [&](int kb) { return kb_fused(kb) ? 4 : 1; };          // TMA-fed K block: one empty slot
-      struct Cur { int kb, i; };
-      auto advance = [&](Cur& k) { if (++k.i == rows_of(k.kb)) { k.i = 0; ++k.kb; } };
-      // meta: bits 0..15 tile row, bit 16 row exists, bit 17 pixel inside the image
-      auto fetch = [&](const Cur& k, float4& a0, float4& a1, int& meta) {
-        a0 = make_float4(0.f, 0.f, 0.f, 0.f); a1 = a0; meta = 0;
-        if (k.kb >= kb_end || !kb_fused(k.kb)) return;
-        const bool main = k.kb < nkb_main;
-        const XfOperand& src = main ? xf.a : xf.x;
-        int dy = 0, dx = 0, ch = k.kb - nkb_main;
-        if (main) {
-          const int tap = k.kb / p.nchunk_main;
-          ch = k.kb - tap * p.nchunk_main;
-          if (p.ntaps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-        }
-        const int r = rr0 + 32 * k.i;
-        const int h = h0 + (r >> xf.tw_shift) + dy, w = w0 + (r & (p.TW - 1)) + dx;
-        const bool inb = h >= 0 && h < p.H && w >= 0 && w < p.W;   // outside: zero padding (what TMA's OOB fill delivers)
-        meta = r | (1 << 16) | (inb ? (1 << 17) : 0);
-        if (!inb) return;
-        const int cg = ch * BK;
-        const float* base; int ld;
-        if (cg < src.C1) { base = src.s1 + cg; ld = src.C1; } else { base = src.s2 + (cg - src.C1); ld = src.C2; }
-        const float4* g = reinterpret_cast<const float4*>(
-            base + (static_cast<size_t>(b) * p.H * p.W + static_cast<size_t>(h) * p.W + w) * ld + j * 8);
-        a0 = __ldg(g); a1 = __ldg(g + 1);
-      };
-      constexpr int kAhead = 4;                // rows in flight per thread: one whole K block
-      float4 qa[kAhead], qb[kAhead];
-      int qm[kAhead];
-      Cur L{kb_begin, 0}, P{kb_begin, 0};
-#pragma unroll
-      for (int d = 0; d < kAhead; ++d) { fetch(L, qa[d], qb[d], qm[d]); advance(L); }
-      if (norm_a) asm volatile("bar.sync 2, 288;" ::: "memory");   // scale / shift table (built by warp 1) is complete
-      float vmax = 0.f;
-      int stage = 0;
-      uint32_t phase = 0;
-#pragma unroll 1
-      while (P.kb < kb_end) {
-        const bool main = P.kb < nkb_main;
-        const bool fused = kb_fused(P.kb);
-        if (P.i == 0) ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-        const int meta = qm[0];
-        if (meta & (1 << 16)) {
-          const int r = meta & 0xffff;
-          uint2 hh0 = make_uint2(0u, 0u), ll0 = hh0, hh1 = hh0, ll1 = hh0;
-          if (meta & (1 << 17)) {
-            float4 a0 = qa[0], a1 = qb[0];
-            if (main && norm_a) {
-              const float* tsc = s_xsc + (P.kb % p.nchunk_main) * BK + j * 8;
-              const float* tsh = s_xsh + (P.kb % p.nchunk_main) * BK + j * 8;
-              a0 = norm_act(a0, *reinterpret_cast<const float4*>(tsc), *reinterpret_cast<const float4*>(tsh), xf.silu);
-              a1 = norm_act(a1, *reinterpret_cast<const float4*>(tsc + 4), *reinterpret_cast<const float4*>(tsh + 4), xf.silu);
-            }
-            split4(a0, hh0, ll0); split4(a1, hh1, ll1);
-            vmax = amax4(a0, amax4(a1, vmax));
-          }
-          const uint32_t dst = smem_base + stage * C::STAGE_BYTES + static_cast<uint32_t>(r) * 128u +
-                               (static_cast<uint32_t>(j ^ (r & 7)) << 4);
-          ptx::st_shared_v4(dst, pack8(hh0, hh1));
-          ptx::st_shared_v4(dst + A_BYTES, pack8(ll0, ll1));
-        }
-#pragma unroll
-        for (int d = 0; d + 1 < kAhead; ++d) { qa[d] = qa[d + 1]; qb[d] = qb[d + 1]; qm[d] = qm[d + 1]; }
-        fetch(L, qa[kAhead - 1], qb[kAhead - 1], qm[kAhead - 1]);
-        advance(L);
-        if (P.i + 1 == rows_of(P.kb)) {                    // last row of the K block: hand the stage to the MMA warp
-          if (fused) ptx::fence_proxy_async();             // generic-proxy stores -> visible to the tensor core's reads
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(full_bar(stage));
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-        }
-        advance(P);
-      }
-      if (vmax > kHalfMax && xf.overflow) atomicAdd(xf.overflow, 1ull);
-    }
 
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after();
@@ -742,7 +591,7 @@ GemmParams make_params(const ConvGemmArgs& a) {
   p.tiles_h = (a.H + p.TH - 1) / p.TH;
   p.nchunk_main = a.Cin / BK;
   p.ntaps = a.ntaps;
-  p.nchunk_sc = (a.X || a.fX.s1) ? a.Cin2 / BK : 0;
+  p.nchunk_sc = a.X ? a.Cin2 / BK : 0;
   p.Cout = a.Cout; p.ldc = a.ldc;
   p.wscale_inv = a.wscale_inv;
   p.bias = a.bias; p.bias_bstride = a.bias_bstride;
@@ -758,7 +607,7 @@ GemmParams make_params(const ConvGemmArgs& a) {
 bool check_args(const ConvGemmArgs& a, std::string* err) {
   auto fail = [&](const char* m) { if (err) *err = std::string("conv_gemm: ") + m; return false; };
   if (a.Cin <= 0 || a.Cin % BK) return fail("Cin must be a positive multiple of 64");
-  if ((a.X || a.fX.s1) && (a.Cin2 <= 0 || a.Cin2 % BK)) return fail("Cin2 must be a positive multiple of 64");
+  if (a.X && (a.Cin2 <= 0 || a.Cin2 % BK)) return fail("Cin2 must be a positive multiple of 64");
   if (a.ntaps != 1 && a.ntaps != 9) return fail("ntaps must be 1 or 9");
   if (a.Cout % 4 || a.ldc % 4) return fail("Cout and ldc must be multiples of 4");
   if (a.Cout > a.Npad) return fail("Cout > Npad");
@@ -769,14 +618,14 @@ bool check_args(const ConvGemmArgs& a, std::string* err) {
 
 // Number of 16-CTA clusters (1,1,16; a non-portable size) of this kernel the device can run concurrently, 0 when the size
 // is not available.  Queried once per instantiation.  Clusters of up to 8 CTAs are always schedulable.
-template <int BN, bool XF>
+template <int BN>
 int max_clusters16() {
   static int cached = -1;
   if (cached >= 0) return cached;
   using C = Cfg<BN>;
   cached = 0;
   if (getenv("FLOWSE_CLUSTER16") && getenv("FLOWSE_CLUSTER16")[0] == '0') return cached;
-  if (cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<BN, XF>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+  if (cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<BN>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
     cudaGetLastError();
     return cached;
   }
@@ -787,49 +636,33 @@ int max_clusters16() {
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 16;
   cfg.attrs = attr; cfg.numAttrs = 1;
   int n = 0;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, conv_gemm_tcgen05_kernel<BN, XF>, &cfg);
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, conv_gemm_tcgen05_kernel<BN>, &cfg);
   if (e != cudaSuccess) cudaGetLastError();
   cached = (e == cudaSuccess) ? n : 0;
   return cached;
 }
 
-template <int BN, bool XF = false>
+template <int BN>
 int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<BN, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
     attr_set = true;
   }
   GemmParams p = make_params(a);
-  const bool has_x = a.X != nullptr || a.fX.s1 != nullptr;
-  const int K = a.ntaps * a.Cin + (has_x ? a.Cin2 : 0);
-  XfParams xf{};
-  if (XF) {
-    xf.a = XfOperand{a.fA.s1, a.fA.s2, a.fA.C1, a.fA.s2 ? a.fA.C2 : 0};
-    xf.x = XfOperand{a.fX.s1, a.fX.s2, a.fX.C1, a.fX.s2 ? a.fX.C2 : 0};
-    xf.qs1 = a.fA.qs1; xf.qs2 = a.fA.qs2; xf.gamma = a.fA.gamma; xf.beta = a.fA.beta; xf.silu = a.fA.silu;
-    xf.overflow = a.overflow;
-    xf.tw_shift = 0;
-    while ((1 << xf.tw_shift) < p.TW) ++xf.tw_shift;
-    auto bad = [&](const char* m) { if (err) *err = std::string("conv_gemm (fused operand): ") + m; return 1; };
-    if (a.fA.s1 && (xf.a.C1 + xf.a.C2 != a.Cin || xf.a.C1 % BK || a.Cin > kXfMaxC)) return bad("main operand channels");
-    if (a.fA.s1 && a.fA.gamma && (!a.fA.beta || !a.fA.qs1 || (xf.a.C2 && !a.fA.qs2))) return bad("GroupNorm parameters / statistics missing");
-    if (a.fX.s1 && (xf.x.C1 + xf.x.C2 != a.Cin2 || xf.x.C1 % BK)) return bad("shortcut operand channels");
-    if (!a.fA.s1 && !a.A) return bad("no main operand");
-  }
+  const int K = a.ntaps * a.Cin + (a.X ? a.Cin2 : 0);
   CUtensorMap tmA, tmX, tmW;
-  if (!make_weight_map(&tmW, a.Wp, a.Npad, K, BN, err)) return 1;
-  if (a.A && !(XF && a.fA.s1)) { if (!make_act_map(&tmA, a.A, a.B, a.H, a.W, a.Cin, p.TW, p.TH, err)) return 1; }
-  else tmA = tmW;                                      // unused: that operand is produced in the kernel
-  if (a.X && !(XF && a.fX.s1)) { if (!make_act_map(&tmX, a.X, a.B, a.H, a.W, a.Cin2, p.TW, p.TH, err)) return 1; }
+  if (!make_act_map(&tmA, a.A, a.B, a.H, a.W, a.Cin, p.TW, p.TH, err)) return 1;
+  if (a.X) { if (!make_act_map(&tmX, a.X, a.B, a.H, a.W, a.Cin2, p.TW, p.TH, err)) return 1; }
   else tmX = tmA;
+  if (!make_weight_map(&tmW, a.Wp, a.Npad, K, BN, err)) return 1;
   dim3 grid(a.B * p.tiles_w * p.tiles_h, (a.Cout + BN - 1) / BN);
   // split-K when the output has too few tiles to fill the GPU (needs ldc == Cout so partial planes are dense)
   const int tiles = grid.x * grid.y;
-  const int nkb_total = a.ntaps * (a.Cin / BK) + (has_x ? a.Cin2 / BK : 0);
+  const int nkb_total = a.ntaps * (a.Cin / BK) + (a.X ? a.Cin2 / BK : 0);
   int S = 1;
   if (a.splitk_scratch && tiles <= 74 && a.ldc == a.Cout && (!a.qstats || 256 % (a.ldc / 4) == 0)) {
     S = std::min(148 / tiles, nkb_total / 4);
@@ -856,7 +689,7 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   }();
   bool cluster_reduce = false;
   if (splitk_mode >= 1 && tiles <= 74 && nkb_total >= 8) {
-    const int max_cluster = (tiles <= max_clusters16<BN, XF>()) ? 16 : 8;
+    const int max_cluster = (tiles <= max_clusters16<BN>()) ? 16 : 8;
     int Sc = std::min(std::min(148 / tiles, nkb_total / 4), max_cluster);
     while (Sc & (Sc - 1)) Sc &= Sc - 1;                  // cluster sizes: powers of two
     if (Sc >= 2) {
@@ -884,7 +717,7 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
     attr[1].val.programmaticStreamSerializationAllowed = pdl_mode() >= 1 ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 2;
     ++launch_counter();
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN, XF>, tmA, tmX, tmW, p, xf);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN>, tmA, tmX, tmW, p);
     if (le != cudaSuccess) { if (err) *err = std::string("conv_gemm cluster launch: ") + cudaGetErrorString(le); return 1; }
   } else {
     cudaLaunchConfig_t cfg{};
@@ -894,7 +727,7 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
     attr[0].val.programmaticStreamSerializationAllowed = pdl_mode() >= 1 ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     ++launch_counter();
-    cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN, XF>, tmA, tmX, tmW, p, xf);
+    cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN>, tmA, tmX, tmW, p);
   }
   if (dbg) {
     cudaStreamSynchronize(s);
@@ -969,10 +802,6 @@ bool make_weight_map(CUtensorMap* m, const __half* base, int Npad, int K, int ro
 
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   if (!check_args(a, err)) return 1;
-  if (a.fA.s1 || a.fX.s1) {
-    if (a.Npad % 128 != 0) { if (err) *err = "conv_gemm: fused operands need Cout tiles of 128"; return 1; }
-    return launch_bn<128, true>(a, s, err);
-  }
   if (a.Npad % 128 == 0) return launch_bn<128>(a, s, err);
   if (a.Npad % 16 == 0) return launch_bn<16>(a, s, err);
   if (err) *err = "conv_gemm: Npad must be a multiple of 16";

@@ -201,7 +201,7 @@ struct flowse_ctx {
   unsigned long long* overflow = nullptr;
   double* rk_acc = nullptr;                 // device accumulator of flowse_rk_lincomb's error norm
   int whole_graph = 1;                      // capture the whole sampler call as one CUDA graph (second call with the same schedule)
-  int fuse_prep = 1;                        // conv kernels prepare their own operands (no standalone prep pass): 1 halo layers, 2 all
+  int fuse_prep = 1;                        // the halo conv kernel prepares its own operands (no standalone prep pass for those layers)
 };
 
 namespace {
@@ -467,11 +467,10 @@ struct Builder {
     // warps, reading the fp32 activations directly.  A resampling block keeps its FIR prep for Conv_0 and for the shortcut
     // operand; its Conv_1 still normalises h1 itself.
     const bool resample = r.up || r.down;
-    // fuse_prep 1: halo-kernel layers only; 2 (default): also the low-resolution layers on the per-tap kernel
-    auto can_fuse = [&](const ConvGemmArgs& c) {
-      if (conv_uses_halo(ctx, c)) return ctx->fuse_prep >= 1;
-      return ctx->fuse_prep >= 2 && ctx->conv_impl == 0 && c.Npad % 128 == 0;
-    };
+    // Only the halo kernel fuses: the same transform in the per-tap kernel (low-resolution layers, 2-10 K blocks per CTA)
+    // was measured 2x slower than prep + TMA - the operand of every K block costs ~3 us to prepare against 0.5 us to fetch
+    // (profiles/README.md, round 2) - and was removed.
+    auto can_fuse = [&](const ConvGemmArgs& c) { return ctx->fuse_prep >= 1 && conv_uses_halo(ctx, c); };
     const bool fuse0 = !resample && can_fuse(c0) && Cin <= 512;
     const bool fuse1 = can_fuse(c1) && Co <= 512;
     if (fuse0) {

@@ -107,8 +107,8 @@ int flowse_fp16_overflow(flowse_ctx* ctx, long long* count, int reset);
  * 4 = like 0 with the CTA-pair (cta_group::2) halo kernel; "graph" 0/1 = replay each NFE as a CUDA graph; "pdl" = programmatic dependent launch (process-wide):
  * 0 off, 1 every kernel, 2 (default) the low-resolution conv launches only - the fastest of the three under graph replay;
  * "whole_graph" 0/1 (default 1) = flowse_sample replays prior + all evaluations + updates as ONE graph from the second call
- * with a given schedule; "fuse_prep" = who prepares the conv operands (GroupNorm + SiLU + fp16 hi/lo split): 0 a standalone
- * pass per conv, 1 the halo conv kernel itself (high-resolution layers), 2 (default) every ResBlock conv kernel. */
+ * with a given schedule; "fuse_prep" = who prepares the conv operands (GroupNorm + SiLU + fp16 hi/lo split) of the
+ * high-resolution layers: 0 a standalone pass per conv, 1 (default) the halo conv kernel itself. */
 int flowse_set_option(flowse_ctx* ctx, const char* key, int value);
 
 /* Number of this library's kernel launches (graph kernel nodes included) since the context was created. */
