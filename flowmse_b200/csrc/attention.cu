@@ -29,6 +29,7 @@ namespace {
 constexpr int kC = 256;          // channels of every attention block of the default config
 constexpr int kR = 8;            // tokens (query rows) per CTA
 constexpr int kThreads = 256;
+constexpr int kStreamU = 16;     // 16-byte loads per thread and batch of the streaming loops (2 batches in flight)
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -153,7 +154,7 @@ attn_qkv_kernel(const QkvK k) {
   float acc[kR][4];
 #pragma unroll
   for (int r = 0; r < kR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
-  stream_fma<8>(acc, k.wqkv + 4 * cq, 3 * kC, &hT[0][0], half * (kC / 2), 1, kC / 2, true);
+  stream_fma<kStreamU>(acc, k.wqkv + 4 * cq, 3 * kC, &hT[0][0], half * (kC / 2), 1, kC / 2, true);
   if (half == 1) {
 #pragma unroll
     for (int r = 0; r < kR; ++r) *reinterpret_cast<float4*>(&red[cq][r][0]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
@@ -232,7 +233,7 @@ attn_core_kernel(const CoreK k) {
       float acc[kR][4];
 #pragma unroll
       for (int r = 0; r < kR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
-      stream_fma<8>(acc, kTb + key, L, qT, half * (kC / 2), 1, kC / 2, live);
+      stream_fma<kStreamU>(acc, kTb + key, L, qT, half * (kC / 2), 1, kC / 2, live);
       if (half == 1) {
 #pragma unroll
         for (int r = 0; r < kR; ++r)
@@ -271,7 +272,7 @@ attn_core_kernel(const CoreK k) {
 #pragma unroll
     for (int r = 0; r < kR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
     const int nkeys = (L - grp + 3) / 4;             // keys grp, grp + 4, ... < L
-    stream_fma<8>(acc, k.v + static_cast<size_t>(b) * L * kC + 4 * cq, kC, Pt, grp, 4, nkeys, true);
+    stream_fma<kStreamU>(acc, k.v + static_cast<size_t>(b) * L * kC + 4 * cq, kC, Pt, grp, 4, nkeys, true);
 #pragma unroll
     for (int r = 0; r < kR; ++r)
       *reinterpret_cast<float4*>(red + (static_cast<size_t>(grp) * kR + r) * kC + 4 * cq) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
@@ -288,7 +289,7 @@ attn_core_kernel(const CoreK k) {
     float acc[kR][4];
 #pragma unroll
     for (int r = 0; r < kR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
-    stream_fma<8>(acc, k.w3 + 4 * cq, kC, oT, grp * (kC / 4), 1, kC / 4, true);
+    stream_fma<kStreamU>(acc, k.w3 + 4 * cq, kC, oT, grp * (kC / 4), 1, kC / 4, true);
     __syncthreads();                                 // everyone has read its share of red
 #pragma unroll
     for (int r = 0; r < kR; ++r)
