@@ -30,7 +30,10 @@
 //    fp16 hi/lo and store the rows at the SAME swizzled addresses TMA would have written (16-byte column j of row r goes
 //    to r*128 + ((j ^ (r & 7)) << 4)); fence.proxy.async + mbarrier arrive hands the stage to the MMA warp.  The
 //    standalone prep kernel (read 4 B + write 4 B per element, 20 % of an evaluation) is gone for these layers and the
-//    operand values are bit-identical to it.  The shortcut operand (raw x, 1 tap) only needs the 128 centre rows.
+//    operand values are bit-identical to it.  The shortcut operand (raw x, 1 tap, the 128 centre rows) is consumed by the
+//    tensor core in ~900 cycles per chunk - far less than a global-memory round trip - so its fp32 tile travels by TMA
+//    through the WEIGHT ring (one extra 32 KB entry in front of the chunk's weight block, prefetched like any other) and
+//    the transform warps split it from shared memory.
 //    Either operand may still come through TMA (after a resampling prep): the producer and the transform warps both
 //    arrive on every stage (count 9), whoever owns the chunk does the work.
 #include "flowse_internal.h"
@@ -190,7 +193,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <int BN, int NMAIN, bool PAIR, bool XF>
 __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX,
-                 const __grid_constant__ CUtensorMap tmW, const HaloParams p, const XfParams xf) {
+                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmR1,
+                 const __grid_constant__ CUtensorMap tmR2, const HaloParams p, const XfParams xf) {
   static_assert(!XF || (!PAIR && NMAIN == 1 && BN == 128), "the fused-operand variant exists for the default tile only");
   using C = HCfg<BN, NMAIN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
@@ -222,6 +226,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const bool is_xf = XF && warp >= w_xf0;
   const bool is_epi = warp >= w_epi0 && warp < w_epi0 + kEpiWarps;
   const int nchunks = p.nchunk_main + p.nchunk_sc;
+  const bool x_raw = XF && xf.x.s1 != nullptr;      // fused shortcut operand: raw fp32 tiles ride the weight ring
   const int rank = PAIR ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   const int item0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int item_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -231,6 +236,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmX);
     ptx::prefetch_tensormap(&tmW);
+    if (XF) { ptx::prefetch_tensormap(&tmR1); ptx::prefetch_tensormap(&tmR2); }
     // XF: the producer thread and every transform warp arrive on each A stage
     for (int s = 0; s < A_STAGES; ++s) { ptx::mbar_init(a_full(s), XF ? 1 + kXfWarps : 1); ptx::mbar_init(a_empty(s), 1); }
     for (int s = 0; s < C::B_STAGES; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
@@ -287,6 +293,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const bool main = c < p.nchunk_main;
           const int ntap = main ? 9 : 1;
           const int pre = ntap > 2 ? 2 : ntap - 1;       // prefetch the next halo while this chunk's taps stream
+          if (!main && x_raw) {
+            // the shortcut chunk's raw fp32 tile {64 ch, 8, 16} = 32 KB, one ring entry ahead of its weight block
+            const int cg = (c - p.nchunk_main) * BK;
+            { const long long c0 = clock64(); ptx::mbar_wait(b_empty(bs), bph ^ 1u); w_pb += clock64() - c0; }
+            ptx::mbar_expect_tx(b_full(bs), C::B_STAGE_BYTES);
+            if (cg < xf.x.C1) ptx::tma_load_4d(&tmR1, b_full(bs), sB(bs), cg, t.w0, t.h0, t.b);
+            else ptx::tma_load_4d(&tmR2, b_full(bs), sB(bs), cg - xf.x.C1, t.w0, t.h0, t.b);
+            if (++bs == C::B_STAGES) { bs = 0; bph ^= 1u; }
+          }
           for (int tp = 0; tp < ntap; ++tp) {
             const int kb = main ? tp * p.nchunk_main + c : 9 * p.nchunk_main + (c - p.nchunk_main);
             { const long long c0 = clock64(); ptx::mbar_wait(b_empty(bs), bph ^ 1u); w_pb += clock64() - c0; }
@@ -349,6 +364,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const bool main = c < p.nchunk_main;
           const int ntap = main ? 9 : 1;
           { const long long c0 = clock64(); ptx::mbar_wait(a_full(as), aph); w_a += clock64() - c0; }
+          if (!main && x_raw) { if (++bs == C::B_STAGES) { bs = 0; bph ^= 1u; } }     // the raw-tile entry belongs to the transform warps
           for (int tp = 0; tp < ntap; ++tp) {
             { const long long c0 = clock64(); ptx::mbar_wait(b_full(bs), bph); w_b += clock64() - c0; }
             ptx::tc_fence_after();
@@ -473,11 +489,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     };
     float4 v0[NB], v1[NB];
     int meta[NB];                              // bits 0..15 operand row, bit 16 row exists, bit 17 pixel inside the image
+    // global loads of a batch of a 3x3 chunk (the 1x1 shortcut chunks come through shared memory, below)
     auto fetch = [&](const Cur& k) {
-      const bool live = k.it < n_my_items && chunk_fused(k.c);
       const bool main = k.c < p.nchunk_main;
-      const XfOperand& src = main ? xf.a : xf.x;
-      const int cg = (main ? k.c : k.c - p.nchunk_main) * BK;
+      const bool live = k.it < n_my_items && main && xf.a.s1 != nullptr;
+      const XfOperand& src = xf.a;
+      const int cg = k.c * BK;
       const float* base = nullptr; int ld = 0;
       if (live) {
         if (cg < src.C1) { base = src.s1 + cg; ld = src.C1; } else { base = src.s2 + (cg - src.C1); ld = src.C2; }
@@ -486,8 +503,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
         const int slot = r0 + 32 * (NB * k.hb + i);            // 0..191
-        const int r = main ? slot : ((slot >> 3) + 1) * HALO_W + (slot & 7) + 1;
-        const bool exists = live && (main ? slot < A_ROWS : slot < BM);
+        const int r = slot;
+        const bool exists = live && slot < A_ROWS;
         const int hy = r / HALO_W, hx = r - hy * HALO_W;
         const int h = k.t.h0 - 1 + hy, w = k.t.w0 - 1 + hx;
         const bool inb = exists && h >= 0 && h < p.H && w >= 0 && w < p.W;
@@ -504,6 +521,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fetch(P);
     int as = 0;
     uint32_t aph = 0;
+    int rbs = 0;                               // the transform warps' position in the weight ring (raw shortcut tiles)
+    uint32_t rbph = 0;
+    auto ring_advance = [&](int n) { for (int i = 0; i < n; ++i) if (++rbs == C::B_STAGES) { rbs = 0; rbph ^= 1u; } };
     int cur_b = -1;
     float vmax = 0.f;
     long long w_xe = 0, w_xp = 0;              // debug: cycles waiting for a free stage / preparing batches
@@ -523,7 +543,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.dbg) w_xe += clock64() - tc0;
       }
       const long long tc1 = p.dbg ? clock64() : 0;
-      if (fused) {
+      if (!main && x_raw) {
+        if (P.hb == 0) {
+          // 1x1 shortcut chunk: its raw fp32 tile [128 rows][64 ch] sits in the weight ring; exact hi / lo split only
+          ptx::mbar_wait(b_full(rbs), rbph);
+          const uint32_t raw = sB(rbs), stage = sA(as);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int idx = r0 + 32 * i;                           // tile row 0..127
+            const float4 a0 = ptx::ld_shared_v4(raw + static_cast<uint32_t>(idx) * 256u + static_cast<uint32_t>(j) * 32u);
+            const float4 a1 = ptx::ld_shared_v4(raw + static_cast<uint32_t>(idx) * 256u + static_cast<uint32_t>(j) * 32u + 16u);
+            uint2 h0, l0, h1, l1;
+            split4(a0, h0, l0); split4(a1, h1, l1);
+            vmax = amax4(a0, amax4(a1, vmax));
+            const int r = ((idx >> 3) + 1) * HALO_W + (idx & 7) + 1;
+            const uint32_t dst = stage + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
+            ptx::st_shared_v4(dst, pack8(h0, h1));
+            ptx::st_shared_v4(dst + A_PLANE_STRIDE, pack8(l0, l1));
+          }
+          named_bar_sync(4, kXfWarps * 32);                        // every transform thread has read the raw tile
+          if (xt == 0) ptx::mbar_arrive(b_empty(rbs));             // back to the producer (the MMA warp skips this entry)
+          ring_advance(2);                                         // the raw tile and the chunk's weight block
+        }
+      } else if (fused) {
         const bool norm = main && norm_a;
         float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
         if (norm) {
@@ -555,7 +597,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool last = P.hb == HB - 1;
       advance(P);
       fetch(P);                                // the registers are free again: the next batch's loads fly during the hand-over
-      if (last) {                              // second batch of the chunk done: hand the stage to the MMA warp
+      if (last) {                              // last batch of the chunk done: hand the stage to the MMA warp
+        if (main) ring_advance(9); else if (!x_raw) ring_advance(1);
         if (fused) ptx::fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(a_full(as));
@@ -749,6 +792,29 @@ bool make_halo_map(CUtensorMap* m, const __half* base, int B, int H, int W, int 
   return true;
 }
 
+// fp32 NHWC source [B][H][W][C] of a fused shortcut operand -> 4-D map, box {64 ch, TW, TH, 1} = one 32 KB raw tile
+// (row-major rows of 256 B, no swizzle: the transform warps read it with plain shared-memory loads)
+bool make_raw_map(CUtensorMap* m, const float* base, int B, int H, int W, int C, std::string* err) {
+  EncodeTiledFn enc = tensor_map_encoder(err);
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(raw B=%d H=%d W=%d C=%d) failed: %d", B, H, W, C, (int)r);
+      *err = buf;
+    }
+    return false;
+  }
+  return true;
+}
+
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -801,6 +867,12 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   else tmA = tmW;                                      // unused: that operand is produced in the kernel
   if (a.X && !(XF && a.fX.s1)) { if (!make_halo_map(&tmX, a.X, a.B, a.H, a.W, a.Cin2, err)) return 1; }
   else tmX = tmA;
+  CUtensorMap tmR1 = tmW, tmR2 = tmW;                  // raw fp32 tiles of a fused shortcut operand (two concat sources)
+  if (XF && a.fX.s1) {
+    static_assert(C::B_STAGE_BYTES == BM * BK * 4 || !XF, "a raw shortcut tile must fill exactly one weight-ring stage");
+    if (!make_raw_map(&tmR1, a.fX.s1, a.B, a.H, a.W, xf.x.C1, err)) return 1;
+    if (xf.x.C2 && !make_raw_map(&tmR2, a.fX.s2, a.B, a.H, a.W, xf.x.C2, err)) return 1;
+  }
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[2];
   cfg.blockDim = dim3(XF ? NUM_THREADS_XF : NUM_THREADS);
@@ -822,7 +894,7 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   long long* dbuf = nullptr;
   const size_t nctas = cfg.gridDim.x;
   if (dbg) { cudaMalloc(&dbuf, nctas * 16 * sizeof(long long)); cudaMemset(dbuf, 0, nctas * 16 * sizeof(long long)); p.dbg = dbuf; }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, NMAIN, PAIR, XF>, tmA, tmX, tmW, p, xf);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, NMAIN, PAIR, XF>, tmA, tmX, tmW, tmR1, tmR2, p, xf);
   ++launch_counter();
   if (dbg) {
     cudaStreamSynchronize(s);
