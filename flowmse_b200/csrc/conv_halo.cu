@@ -198,7 +198,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   static_assert(!XF || (!PAIR && NMAIN == 1 && BN == 128), "the fused-operand variant exists for the default tile only");
   using C = HCfg<BN, NMAIN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
-  constexpr int NBARS = 2 * A_STAGES + 2 * C::B_STAGES + 2 * C::NBUF;
+  constexpr int NBARS = 2 * A_STAGES + 2 * C::B_STAGES + 2 * C::NBUF + (XF ? C::B_STAGES : 0);
   __shared__ uint64_t bars[NBARS];
   __shared__ uint32_t tmem_slot_var;
   __shared__ float s_qs[2][kEpiWarps][C::COLS_PER_WARP / 4 > 0 ? C::COLS_PER_WARP / 4 : 1][2];
@@ -212,6 +212,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * A_STAGES + C::B_STAGES + s); };
   auto t_full = [&](int s) { return bar_base + 8u * (2 * A_STAGES + 2 * C::B_STAGES + s); };
   auto t_empty = [&](int s) { return bar_base + 8u * (2 * A_STAGES + 2 * C::B_STAGES + C::NBUF + s); };
+  // XF: "a raw shortcut tile has been ISSUED into weight-ring stage s".  The transform warps do not follow the weight ring
+  // entry by entry, so a parity wait on b_full alone could be satisfied by an OLDER phase of the stage (a parity wait is
+  // only exact when the waiter is at most one phase ahead); this per-stage barrier, whose phases they do observe one by
+  // one, tells them that b_full(s) has entered the raw tile's phase.
+  auto x_iss = [&](int s) { return bar_base + 8u * (2 * A_STAGES + 2 * C::B_STAGES + 2 * C::NBUF + s); };
   auto sA = [&](int s) { return smem_base + static_cast<uint32_t>(s) * A_STAGE_BYTES; };
   auto sB = [&](int s) { return smem_base + A_STAGES * A_STAGE_BYTES + static_cast<uint32_t>(s) * C::B_STAGE_BYTES; };
   const uint32_t tmem_slot = ptx::smem_u32(&tmem_slot_var);
@@ -241,6 +246,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < A_STAGES; ++s) { ptx::mbar_init(a_full(s), XF ? 1 + kXfWarps : 1); ptx::mbar_init(a_empty(s), 1); }
     for (int s = 0; s < C::B_STAGES; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
     for (int s = 0; s < C::NBUF; ++s) { ptx::mbar_init(t_full(s), 1); ptx::mbar_init(t_empty(s), kEpiWarps * kCtas); }
+    if constexpr (XF) for (int s = 0; s < C::B_STAGES; ++s) ptx::mbar_init(x_iss(s), 1);
     ptx::fence_mbar_init();
   }
   if (warp == w_alloc) {
@@ -264,7 +270,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       auto full_addr = [&](uint32_t local) { return PAIR ? ptx::map_to_cta(local, 0) : local; };
       auto issue_A = [&](int item, int c) {
         const TileCoord t = decode_tile<BN, PAIR>(p, item, rank);
-        { const long long c0 = clock64(); ptx::mbar_wait(a_empty(as), aph ^ 1u); w_pa += clock64() - c0; }
+        { const long long c0 = clock64(); FLOWSE_MBAR_WAIT(a_empty(as), aph ^ 1u, 1); w_pa += clock64() - c0; }
         const bool main = c < p.nchunk_main;
         if (XF && (main ? xf.a.s1 : xf.x.s1) != nullptr) {
           ptx::mbar_arrive(a_full(as));              // the transform warps fill this stage
@@ -296,15 +302,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!main && x_raw) {
             // the shortcut chunk's raw fp32 tile {64 ch, 8, 16} = 32 KB, one ring entry ahead of its weight block
             const int cg = (c - p.nchunk_main) * BK;
-            { const long long c0 = clock64(); ptx::mbar_wait(b_empty(bs), bph ^ 1u); w_pb += clock64() - c0; }
+            { const long long c0 = clock64(); FLOWSE_MBAR_WAIT(b_empty(bs), bph ^ 1u, 2); w_pb += clock64() - c0; }
             ptx::mbar_expect_tx(b_full(bs), C::B_STAGE_BYTES);
             if (cg < xf.x.C1) ptx::tma_load_4d(&tmR1, b_full(bs), sB(bs), cg, t.w0, t.h0, t.b);
             else ptx::tma_load_4d(&tmR2, b_full(bs), sB(bs), cg - xf.x.C1, t.w0, t.h0, t.b);
+            if constexpr (XF) ptx::mbar_arrive(x_iss(bs));           // b_full(bs) is now in this tile's phase
             if (++bs == C::B_STAGES) { bs = 0; bph ^= 1u; }
           }
           for (int tp = 0; tp < ntap; ++tp) {
             const int kb = main ? tp * p.nchunk_main + c : 9 * p.nchunk_main + (c - p.nchunk_main);
-            { const long long c0 = clock64(); ptx::mbar_wait(b_empty(bs), bph ^ 1u); w_pb += clock64() - c0; }
+            { const long long c0 = clock64(); FLOWSE_MBAR_WAIT(b_empty(bs), bph ^ 1u, 3); w_pb += clock64() - c0; }
             if (rank == 0) ptx::mbar_expect_tx(b_full(bs), C::B_STAGE_BYTES * kCtas);
             const uint32_t bar = full_addr(b_full(bs));
             if constexpr (PAIR) {
@@ -355,7 +362,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int item = item0; item < p.num_items; item += item_stride, ++it) {
         const int buf = it % C::NBUF;
         const uint32_t use = static_cast<uint32_t>(it / C::NBUF);
-        { const long long c0 = clock64(); ptx::mbar_wait(t_empty(buf), (use & 1u) ^ 1u); w_t += clock64() - c0; }   // epilogue has drained this accumulator buffer
+        { const long long c0 = clock64(); FLOWSE_MBAR_WAIT(t_empty(buf), (use & 1u) ^ 1u, 4); w_t += clock64() - c0; }   // epilogue has drained this accumulator buffer
         ptx::tc_fence_after();
         const uint32_t acc = tmem_acc + static_cast<uint32_t>(buf * C::NSLOT * C::SLOT_COLS);
         const uint32_t d_corr = acc + static_cast<uint32_t>(NMAIN * C::SLOT_COLS);
@@ -363,10 +370,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = 0; c < nchunks; ++c) {
           const bool main = c < p.nchunk_main;
           const int ntap = main ? 9 : 1;
-          { const long long c0 = clock64(); ptx::mbar_wait(a_full(as), aph); w_a += clock64() - c0; }
+          { const long long c0 = clock64(); FLOWSE_MBAR_WAIT(a_full(as), aph, 5); w_a += clock64() - c0; }
           if (!main && x_raw) { if (++bs == C::B_STAGES) { bs = 0; bph ^= 1u; } }     // the raw-tile entry belongs to the transform warps
           for (int tp = 0; tp < ntap; ++tp) {
-            { const long long c0 = clock64(); ptx::mbar_wait(b_full(bs), bph); w_b += clock64() - c0; }
+            { const long long c0 = clock64(); FLOWSE_MBAR_WAIT(b_full(bs), bph, 6); w_b += clock64() - c0; }
             ptx::tc_fence_after();
             // view of the halo for this tap: rows shifted by (dy+1) halo rows and (dx+1) pixels
             const int shift = main ? (tp / 3) * HALO_W + (tp % 3) : HALO_W + 1;
@@ -523,6 +530,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t aph = 0;
     int rbs = 0;                               // the transform warps' position in the weight ring (raw shortcut tiles)
     uint32_t rbph = 0;
+    uint32_t xph = 0;                          // phase bit per ring stage of x_iss
     auto ring_advance = [&](int n) { for (int i = 0; i < n; ++i) if (++rbs == C::B_STAGES) { rbs = 0; rbph ^= 1u; } };
     int cur_b = -1;
     float vmax = 0.f;
@@ -539,14 +547,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           cur_b = P.t.b;
         }
         const long long tc0 = p.dbg ? clock64() : 0;
-        ptx::mbar_wait(a_empty(as), aph ^ 1u);
+        FLOWSE_MBAR_WAIT(a_empty(as), aph ^ 1u, 7);
         if (p.dbg) w_xe += clock64() - tc0;
       }
       const long long tc1 = p.dbg ? clock64() : 0;
       if (!main && x_raw) {
         if (P.hb == 0) {
           // 1x1 shortcut chunk: its raw fp32 tile [128 rows][64 ch] sits in the weight ring; exact hi / lo split only
-          ptx::mbar_wait(b_full(rbs), rbph);
+          if constexpr (XF) { FLOWSE_MBAR_WAIT(x_iss(rbs), (xph >> rbs) & 1u, 10); xph ^= 1u << rbs; }
+          FLOWSE_MBAR_WAIT(b_full(rbs), rbph, 8);
           const uint32_t raw = sB(rbs), stage = sA(as);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -660,7 +669,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       };
       if (active) load_res(0);
 
-      ptx::mbar_wait(t_full(buf), use & 1u);
+      FLOWSE_MBAR_WAIT(t_full(buf), use & 1u, 9);
       ptx::tc_fence_after();
       const uint32_t acc = tmem_acc + static_cast<uint32_t>(buf * C::NSLOT * C::SLOT_COLS);
 
