@@ -30,10 +30,7 @@
 //    fp16 hi/lo and store the rows at the SAME swizzled addresses TMA would have written (16-byte column j of row r goes
 //    to r*128 + ((j ^ (r & 7)) << 4)); fence.proxy.async + mbarrier arrive hands the stage to the MMA warp.  The
 //    standalone prep kernel (read 4 B + write 4 B per element, 20 % of an evaluation) is gone for these layers and the
-//    operand values are bit-identical to it.  The shortcut operand (raw x, 1 tap, the 128 centre rows) is consumed by the
-//    tensor core in ~900 cycles per chunk - far less than a global-memory round trip - so its fp32 tile travels by TMA
-//    through the WEIGHT ring (one extra 32 KB entry in front of the chunk's weight block, prefetched like any other) and
-//    the transform warps split it from shared memory.
+//    operand values are bit-identical to it.  The shortcut operand (raw x, 1 tap) only needs the 128 centre rows.
 //    Either operand may still come through TMA (after a resampling prep): the producer and the transform warps both
 //    arrive on every stage (count 9), whoever owns the chunk does the work.
 #include "flowse_internal.h"
@@ -193,12 +190,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <int BN, int NMAIN, bool PAIR, bool XF>
 __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX,
-                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmR1,
-                 const __grid_constant__ CUtensorMap tmR2, const HaloParams p, const XfParams xf) {
+                 const __grid_constant__ CUtensorMap tmW, const HaloParams p, const XfParams xf) {
   static_assert(!XF || (!PAIR && NMAIN == 1 && BN == 128), "the fused-operand variant exists for the default tile only");
   using C = HCfg<BN, NMAIN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
-  constexpr int NBARS = 2 * A_STAGES + 2 * C::B_STAGES + 2 * C::NBUF + (XF ? C::B_STAGES : 0);
+  constexpr int NBARS = 2 * A_STAGES + 2 * C::B_STAGES + 2 * C::NBUF;
   __shared__ uint64_t bars[NBARS];
   __shared__ uint32_t tmem_slot_var;
   __shared__ float s_qs[2][kEpiWarps][C::COLS_PER_WARP / 4 > 0 ? C::COLS_PER_WARP / 4 : 1][2];
@@ -212,11 +208,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * A_STAGES + C::B_STAGES + s); };
   auto t_full = [&](int s) { return bar_base + 8u * (2 * A_STAGES + 2 * C::B_STAGES + s); };
   auto t_empty = [&](int s) { return bar_base + 8u * (2 * A_STAGES + 2 * C::B_STAGES + C::NBUF + s); };
-  // XF: "a raw shortcut tile has been ISSUED into weight-ring stage s".  The transform warps do not follow the weight ring
-  // entry by entry, so a parity wait on b_full alone could be satisfied by an OLDER phase of the stage (a parity wait is
-  // only exact when the waiter is at most one phase ahead); this per-stage barrier, whose phases they do observe one by
-  // one, tells them that b_full(s) has entered the raw tile's phase.
-  auto x_iss = [&](int s) { return bar_base + 8u * (2 * A_STAGES + 2 * C::B_STAGES + 2 * C::NBUF + s); };
   auto sA = [&](int s) { return smem_base + static_cast<uint32_t>(s) * A_STAGE_BYTES; };
   auto sB = [&](int s) { return smem_base + A_STAGES * A_STAGE_BYTES + static_cast<uint32_t>(s) * C::B_STAGE_BYTES; };
   const uint32_t tmem_slot = ptx::smem_u32(&tmem_slot_var);
@@ -231,7 +222,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const bool is_xf = XF && warp >= w_xf0;
   const bool is_epi = warp >= w_epi0 && warp < w_epi0 + kEpiWarps;
   const int nchunks = p.nchunk_main + p.nchunk_sc;
-  const bool x_raw = XF && xf.x.s1 != nullptr;      // fused shortcut operand: raw fp32 tiles ride the weight ring
   const int rank = PAIR ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   const int item0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int item_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -241,12 +231,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmX);
     ptx::prefetch_tensormap(&tmW);
-    if (XF) { ptx::prefetch_tensormap(&tmR1); ptx::prefetch_tensormap(&tmR2); }
     // XF: the producer thread and every transform warp arrive on each A stage
     for (int s = 0; s < A_STAGES; ++s) { ptx::mbar_init(a_full(s), XF ? 1 + kXfWarps : 1); ptx::mbar_init(a_empty(s), 1); }
     for (int s = 0; s < C::B_STAGES; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
     for (int s = 0; s < C::NBUF; ++s) { ptx::mbar_init(t_full(s), 1); ptx::mbar_init(t_empty(s), kEpiWarps * kCtas); }
-    if constexpr (XF) for (int s = 0; s < C::B_STAGES; ++s) ptx::mbar_init(x_iss(s), 1);
     ptx::fence_mbar_init();
   }
   if (warp == w_alloc) {
@@ -270,7 +258,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       auto full_addr = [&](uint32_t local) { return PAIR ? ptx::map_to_cta(local, 0) : local; };
       auto issue_A = [&](int item, int c) {
         const TileCoord t = decode_tile<BN, PAIR>(p, item, rank);
-        { const long long c0 = clock64(); FLOWSE_MBAR_WAIT(a_empty(as), aph ^ 1u, 1); w_pa += clock64() - c0; }
+        { const long long c0 = clock64(); ptx::mbar_wait(a_empty(as), aph ^ 1u); w_pa += clock64() - c0; }
         const bool main = c < p.nchunk_main;
         if (XF && (main ? xf.a.s1 : xf.x.s1) != nullptr) {
           ptx::mbar_arrive(a_full(as));              // the transform warps fill this stage
@@ -299,19 +287,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const bool main = c < p.nchunk_main;
           const int ntap = main ? 9 : 1;
           const int pre = ntap > 2 ? 2 : ntap - 1;       // prefetch the next halo while this chunk's taps stream
-          if (!main && x_raw) {
-            // the shortcut chunk's raw fp32 tile {64 ch, 8, 16} = 32 KB, one ring entry ahead of its weight block
-            const int cg = (c - p.nchunk_main) * BK;
-            { const long long c0 = clock64(); FLOWSE_MBAR_WAIT(b_empty(bs), bph ^ 1u, 2); w_pb += clock64() - c0; }
-            ptx::mbar_expect_tx(b_full(bs), C::B_STAGE_BYTES);
-            if (cg < xf.x.C1) ptx::tma_load_4d(&tmR1, b_full(bs), sB(bs), cg, t.w0, t.h0, t.b);
-            else ptx::tma_load_4d(&tmR2, b_full(bs), sB(bs), cg - xf.x.C1, t.w0, t.h0, t.b);
-            if constexpr (XF) ptx::mbar_arrive(x_iss(bs));           // b_full(bs) is now in this tile's phase
-            if (++bs == C::B_STAGES) { bs = 0; bph ^= 1u; }
-          }
           for (int tp = 0; tp < ntap; ++tp) {
             const int kb = main ? tp * p.nchunk_main + c : 9 * p.nchunk_main + (c - p.nchunk_main);
-            { const long long c0 = clock64(); FLOWSE_MBAR_WAIT(b_empty(bs), bph ^ 1u, 3); w_pb += clock64() - c0; }
+            { const long long c0 = clock64(); ptx::mbar_wait(b_empty(bs), bph ^ 1u); w_pb += clock64() - c0; }
             if (rank == 0) ptx::mbar_expect_tx(b_full(bs), C::B_STAGE_BYTES * kCtas);
             const uint32_t bar = full_addr(b_full(bs));
             if constexpr (PAIR) {
@@ -362,7 +340,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int item = item0; item < p.num_items; item += item_stride, ++it) {
         const int buf = it % C::NBUF;
         const uint32_t use = static_cast<uint32_t>(it / C::NBUF);
-        { const long long c0 = clock64(); FLOWSE_MBAR_WAIT(t_empty(buf), (use & 1u) ^ 1u, 4); w_t += clock64() - c0; }   // epilogue has drained this accumulator buffer
+        { const long long c0 = clock64(); ptx::mbar_wait(t_empty(buf), (use & 1u) ^ 1u); w_t += clock64() - c0; }   // epilogue has drained this accumulator buffer
         ptx::tc_fence_after();
         const uint32_t acc = tmem_acc + static_cast<uint32_t>(buf * C::NSLOT * C::SLOT_COLS);
         const uint32_t d_corr = acc + static_cast<uint32_t>(NMAIN * C::SLOT_COLS);
@@ -370,10 +348,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = 0; c < nchunks; ++c) {
           const bool main = c < p.nchunk_main;
           const int ntap = main ? 9 : 1;
-          { const long long c0 = clock64(); FLOWSE_MBAR_WAIT(a_full(as), aph, 5); w_a += clock64() - c0; }
-          if (!main && x_raw) { if (++bs == C::B_STAGES) { bs = 0; bph ^= 1u; } }     // the raw-tile entry belongs to the transform warps
+          { const long long c0 = clock64(); ptx::mbar_wait(a_full(as), aph); w_a += clock64() - c0; }
           for (int tp = 0; tp < ntap; ++tp) {
-            { const long long c0 = clock64(); FLOWSE_MBAR_WAIT(b_full(bs), bph, 6); w_b += clock64() - c0; }
+            { const long long c0 = clock64(); ptx::mbar_wait(b_full(bs), bph); w_b += clock64() - c0; }
             ptx::tc_fence_after();
             // view of the halo for this tap: rows shifted by (dy+1) halo rows and (dx+1) pixels
             const int shift = main ? (tp / 3) * HALO_W + (tp % 3) : HALO_W + 1;
@@ -496,12 +473,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     };
     float4 v0[NB], v1[NB];
     int meta[NB];                              // bits 0..15 operand row, bit 16 row exists, bit 17 pixel inside the image
-    // global loads of a batch of a 3x3 chunk (the 1x1 shortcut chunks come through shared memory, below)
     auto fetch = [&](const Cur& k) {
+      const bool live = k.it < n_my_items && chunk_fused(k.c);
       const bool main = k.c < p.nchunk_main;
-      const bool live = k.it < n_my_items && main && xf.a.s1 != nullptr;
-      const XfOperand& src = xf.a;
-      const int cg = k.c * BK;
+      const XfOperand& src = main ? xf.a : xf.x;
+      const int cg = (main ? k.c : k.c - p.nchunk_main) * BK;
       const float* base = nullptr; int ld = 0;
       if (live) {
         if (cg < src.C1) { base = src.s1 + cg; ld = src.C1; } else { base = src.s2 + (cg - src.C1); ld = src.C2; }
@@ -510,8 +486,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
         const int slot = r0 + 32 * (NB * k.hb + i);            // 0..191
-        const int r = slot;
-        const bool exists = live && slot < A_ROWS;
+        const int r = main ? slot : ((slot >> 3) + 1) * HALO_W + (slot & 7) + 1;
+        const bool exists = live && (main ? slot < A_ROWS : slot < BM);
         const int hy = r / HALO_W, hx = r - hy * HALO_W;
         const int h = k.t.h0 - 1 + hy, w = k.t.w0 - 1 + hx;
         const bool inb = exists && h >= 0 && h < p.H && w >= 0 && w < p.W;
@@ -528,10 +504,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fetch(P);
     int as = 0;
     uint32_t aph = 0;
-    int rbs = 0;                               // the transform warps' position in the weight ring (raw shortcut tiles)
-    uint32_t rbph = 0;
-    uint32_t xph = 0;                          // phase bit per ring stage of x_iss
-    auto ring_advance = [&](int n) { for (int i = 0; i < n; ++i) if (++rbs == C::B_STAGES) { rbs = 0; rbph ^= 1u; } };
     int cur_b = -1;
     float vmax = 0.f;
     long long w_xe = 0, w_xp = 0;              // debug: cycles waiting for a free stage / preparing batches
@@ -547,34 +519,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           cur_b = P.t.b;
         }
         const long long tc0 = p.dbg ? clock64() : 0;
-        FLOWSE_MBAR_WAIT(a_empty(as), aph ^ 1u, 7);
+        ptx::mbar_wait(a_empty(as), aph ^ 1u);
         if (p.dbg) w_xe += clock64() - tc0;
       }
       const long long tc1 = p.dbg ? clock64() : 0;
-      if (!main && x_raw) {
-        if (P.hb == 0) {
-          // 1x1 shortcut chunk: its raw fp32 tile [128 rows][64 ch] sits in the weight ring; exact hi / lo split only
-          if constexpr (XF) { FLOWSE_MBAR_WAIT(x_iss(rbs), (xph >> rbs) & 1u, 10); xph ^= 1u << rbs; }
-          FLOWSE_MBAR_WAIT(b_full(rbs), rbph, 8);
-          const uint32_t raw = sB(rbs), stage = sA(as);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int idx = r0 + 32 * i;                           // tile row 0..127
-            const float4 a0 = ptx::ld_shared_v4(raw + static_cast<uint32_t>(idx) * 256u + static_cast<uint32_t>(j) * 32u);
-            const float4 a1 = ptx::ld_shared_v4(raw + static_cast<uint32_t>(idx) * 256u + static_cast<uint32_t>(j) * 32u + 16u);
-            uint2 h0, l0, h1, l1;
-            split4(a0, h0, l0); split4(a1, h1, l1);
-            vmax = amax4(a0, amax4(a1, vmax));
-            const int r = ((idx >> 3) + 1) * HALO_W + (idx & 7) + 1;
-            const uint32_t dst = stage + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
-            ptx::st_shared_v4(dst, pack8(h0, h1));
-            ptx::st_shared_v4(dst + A_PLANE_STRIDE, pack8(l0, l1));
-          }
-          named_bar_sync(4, kXfWarps * 32);                        // every transform thread has read the raw tile
-          if (xt == 0) ptx::mbar_arrive(b_empty(rbs));             // back to the producer (the MMA warp skips this entry)
-          ring_advance(2);                                         // the raw tile and the chunk's weight block
-        }
-      } else if (fused) {
+      if (fused) {
         const bool norm = main && norm_a;
         float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
         if (norm) {
@@ -606,8 +555,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool last = P.hb == HB - 1;
       advance(P);
       fetch(P);                                // the registers are free again: the next batch's loads fly during the hand-over
-      if (last) {                              // last batch of the chunk done: hand the stage to the MMA warp
-        if (main) ring_advance(9); else if (!x_raw) ring_advance(1);
+      if (last) {                              // second batch of the chunk done: hand the stage to the MMA warp
         if (fused) ptx::fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(a_full(as));
@@ -669,7 +617,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       };
       if (active) load_res(0);
 
-      FLOWSE_MBAR_WAIT(t_full(buf), use & 1u, 9);
+      ptx::mbar_wait(t_full(buf), use & 1u);
       ptx::tc_fence_after();
       const uint32_t acc = tmem_acc + static_cast<uint32_t>(buf * C::NSLOT * C::SLOT_COLS);
 
@@ -801,29 +749,6 @@ bool make_halo_map(CUtensorMap* m, const __half* base, int B, int H, int W, int 
   return true;
 }
 
-// fp32 NHWC source [B][H][W][C] of a fused shortcut operand -> 4-D map, box {64 ch, TW, TH, 1} = one 32 KB raw tile
-// (row-major rows of 256 B, no swizzle: the transform warps read it with plain shared-memory loads)
-bool make_raw_map(CUtensorMap* m, const float* base, int B, int H, int W, int C, std::string* err) {
-  EncodeTiledFn enc = tensor_map_encoder(err);
-  if (!enc) return false;
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    if (err) {
-      char buf[256];
-      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(raw B=%d H=%d W=%d C=%d) failed: %d", B, H, W, C, (int)r);
-      *err = buf;
-    }
-    return false;
-  }
-  return true;
-}
-
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -876,12 +801,6 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   else tmA = tmW;                                      // unused: that operand is produced in the kernel
   if (a.X && !(XF && a.fX.s1)) { if (!make_halo_map(&tmX, a.X, a.B, a.H, a.W, a.Cin2, err)) return 1; }
   else tmX = tmA;
-  CUtensorMap tmR1 = tmW, tmR2 = tmW;                  // raw fp32 tiles of a fused shortcut operand (two concat sources)
-  if (XF && a.fX.s1) {
-    static_assert(C::B_STAGE_BYTES == BM * BK * 4 || !XF, "a raw shortcut tile must fill exactly one weight-ring stage");
-    if (!make_raw_map(&tmR1, a.fX.s1, a.B, a.H, a.W, xf.x.C1, err)) return 1;
-    if (xf.x.C2 && !make_raw_map(&tmR2, a.fX.s2, a.B, a.H, a.W, xf.x.C2, err)) return 1;
-  }
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[2];
   cfg.blockDim = dim3(XF ? NUM_THREADS_XF : NUM_THREADS);
@@ -903,7 +822,7 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   long long* dbuf = nullptr;
   const size_t nctas = cfg.gridDim.x;
   if (dbg) { cudaMalloc(&dbuf, nctas * 16 * sizeof(long long)); cudaMemset(dbuf, 0, nctas * 16 * sizeof(long long)); p.dbg = dbuf; }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, NMAIN, PAIR, XF>, tmA, tmX, tmW, tmR1, tmR2, p, xf);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, NMAIN, PAIR, XF>, tmA, tmX, tmW, p, xf);
   ++launch_counter();
   if (dbg) {
     cudaStreamSynchronize(s);

@@ -4,7 +4,6 @@
 // cute/arch/mma_sm100_desc.hpp).
 #pragma once
 #include <cstdint>
-#include <cstdio>
 #include <cuda.h>
 
 namespace ptx {
@@ -68,35 +67,6 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-#ifdef FLOWSE_MBAR_DEBUG
-// Debug build: a wait that exceeds 1 s reports who was waiting for what and RETURNS (the kernel then finishes with garbage,
-// so the message is flushed) instead of trapping.
-#define FLOWSE_MBAR_WAIT(bar, parity, tag) ptx::mbar_wait_dbg(bar, parity, tag)
-__device__ __forceinline__ void mbar_wait_dbg(uint32_t bar, uint32_t parity, int tag) {
-  uint32_t ok = 0;
-  uint64_t t0 = 0;
-  for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) return;
-    if ((it & 0x3ff) == 0x3ff) {
-      uint64_t now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 1000000000ull) {
-        if ((threadIdx.x & 31) == 0)
-          printf("[mbar timeout] tag %d block %d warp %d bar 0x%x parity %u\n", tag, blockIdx.x, threadIdx.x >> 5, bar, parity);
-        return;
-      }
-    }
-  }
-}
-#else
-#define FLOWSE_MBAR_WAIT(bar, parity, tag) ptx::mbar_wait(bar, parity)
-#endif
-
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -106,18 +76,6 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint32_t bar, 
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint32_t bar, uint32_t dst,
-                                            int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
 }
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint32_t bar, uint32_t dst,
                                             int c0, int c1, int c2, int c3, int c4) {
