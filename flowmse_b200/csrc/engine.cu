@@ -122,7 +122,13 @@ struct Act { float* p = nullptr; int C = 0, H = 0, W = 0; double* qs = nullptr; 
 
 // kind: 0 misc, 1 gn_stats, 2 gn_prep, 3 conv_gemm (per-tap kernel), 4 attention, 5 small 4-channel / input kernels,
 //       6 time embedding, 7 conv_halo (halo kernel; chosen at plan time with the conv_impl option in force)
-struct Op { std::function<int(cudaStream_t)> fn; int nk; int kind; double flops; int info[4]; };
+// branch: 0 = the main chain; 1 = output pyramid (the heads read h of the main chain and the previous head: nothing on the
+// main chain needs them before the final kernel); 2 = input pyramid (the FIR-downsample chain depends only on the input).
+// Under graph capture the side branches become parallel graph branches: they fill the SMs the short low-resolution
+// kernels of the main chain leave idle.  needs_main: wait for the main chain's current position; wait_branch: a main op
+// that consumes what the branch has produced so far.
+struct Op { std::function<int(cudaStream_t)> fn; int nk; int kind; double flops; int info[4]; int branch = 0; bool needs_main = true;
+            int wait_branch = 0; };
 
 struct Plan;
 void destroy_graphs(Plan* p);
@@ -186,6 +192,9 @@ struct flowse_ctx {
   long long counter_base = 0;
   std::unique_ptr<Plan> plan;
   cudaStream_t cap_stream = nullptr;   // capture happens here: the caller's stream may be the legacy default stream
+  cudaStream_t side[2] = {nullptr, nullptr};          // side branches of the captured graphs (output / input pyramid)
+  cudaEvent_t ev_main = nullptr, ev_branch[3] = {nullptr, nullptr, nullptr};
+  int fork_branches = 1;                              // option "fork": capture the pyramid branches as parallel graph branches
   // scratch for op-level entry points
   double* op_stats = nullptr; double* op_partials = nullptr; unsigned* op_counters = nullptr;
   float* op_scratch = nullptr; size_t op_scratch_bytes = 0;
@@ -420,6 +429,9 @@ struct Builder {
             int i2 = 0, int i3 = 0) {
     if (!dry) plan->ops.push_back(Op{std::move(fn), nk, kind, flops, {i0, i1, i2, i3}});
   }
+  void tag_last(int branch, bool needs_main, int wait_branch = 0) {
+    if (!dry) { Op& o = plan->ops.back(); o.branch = branch; o.needs_main = needs_main; o.wait_branch = wait_branch; }
+  }
   static double conv_flops(const ConvGemmArgs& a) {
     const double K = static_cast<double>(a.ntaps) * a.Cin + a.Cin2;      // Cin2 = 0 without a folded shortcut
     return 2.0 * a.B * a.H * a.W * a.Cout * K;
@@ -571,6 +583,13 @@ struct Builder {
     }
     plan->taps[3] = h0;
     ++m;
+    // input pyramid (ncsnpp.py:310): the six FIR downsamples depend on nothing but the input conv's 4-plane copy, so they
+    // are queued here as a side branch instead of one by one in front of their Combine
+    for (int l = 0; l + 1 < kNumLevels; ++l) {
+      const float4* src = pin[l]; float4* dst = pin[l + 1]; const int Bc = B, Hh = H0 >> (l + 1), Ww = W0 >> (l + 1);
+      push(1, [=](cudaStream_t s) { launch_fir_down4(src, dst, Bc, Hh, Ww, s); return 0; }, 5);
+      tag_last(2, l == 0);
+    }
     std::vector<Act> hs = {h0};
     Act h = h0;
     for (int l = 0; l < kNumLevels; ++l) {
@@ -584,10 +603,10 @@ struct Builder {
         const CombW& cw = ctx->combs.at(m);
         Act o = new_act(cw.c, h.H, h.W);
         {
-          const float4* src = pin[l]; float4* dst = pin[l + 1]; const int Bc = B, Hh = h.H, Ww = h.W, C = cw.c;
+          float4* dst = pin[l + 1]; const int Bc = B, Hh = h.H, Ww = h.W, C = cw.c;
           const float* hp = h.p; float* op = o.p; const float *w = cw.w, *bb = cw.b; double* oq = o.qs;
-          push(1, [=](cudaStream_t s) { launch_fir_down4(src, dst, Bc, Hh, Ww, s); return 0; }, 5);
           push(1, [=](cudaStream_t s) { launch_combine(hp, dst, w, bb, op, oq, Bc, Hh, Ww, C, s); return 0; }, 5);
+          tag_last(0, true, 2);
         }
         plan->taps[m] = o;
         h = o; ++m;
@@ -614,6 +633,7 @@ struct Builder {
         // GN + SiLU + conv3x3(C -> 4) + FIR-up(previous level) in one fp32 SIMT kernel
         push(1, [=](cudaStream_t s) { launch_head_conv(hp, hq, gg, gb, wf, hb, prev, pyr, Bc, Hh, Ww, C, s); return 0; },
              5, 2.0 * Bc * Hh * Ww * 4 * 9.0 * C, Hh, Ww, 9 * C, 4);
+        if (l != 0) tag_last(1, true);              // the full-resolution head is the last op before the final kernel anyway
         Act tp; tp.p = reinterpret_cast<float*>(pyr); tp.C = 4; tp.H = Hh; tp.W = Ww;
         plan->taps[m + 1] = tp;
         pyr_prev = pyr;
@@ -678,10 +698,34 @@ int ensure_plan(flowse_ctx* ctx, int B, int T, cudaStream_t s) {
   return 0;
 }
 
-// run the backbone ops eagerly on s
-int run_ops(flowse_ctx* ctx, cudaStream_t s) {
-  for (auto& op : ctx->plan->ops)
-    if (int rc = op.fn(s)) { if (ctx->err.empty()) ctx->err = "plan op failed"; return rc; }
+// Enqueue the backbone ops on s.  fork (only while s is being captured): ops tagged with a side branch go to side streams
+// that fork from / join s through events, i.e. they become parallel branches of the captured graph.
+int run_ops(flowse_ctx* ctx, cudaStream_t s, bool fork = false) {
+  if (fork && !ctx->ev_main) {
+    for (auto& st : ctx->side) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
+    for (int b = 1; b < 3; ++b) CK(cudaEventCreateWithFlags(&ctx->ev_branch[b], cudaEventDisableTiming));
+  }
+  bool used[3] = {false, false, false};
+  for (auto& op : ctx->plan->ops) {
+    int rc;
+    if (!fork || op.branch == 0) {
+      if (fork && op.wait_branch && used[op.wait_branch]) CK(cudaStreamWaitEvent(s, ctx->ev_branch[op.wait_branch], 0));
+      rc = op.fn(s);
+    } else {
+      cudaStream_t sb = ctx->side[op.branch - 1];
+      if (op.needs_main || !used[op.branch]) {          // (the first op of a branch joins the capture through this edge)
+        CK(cudaEventRecord(ctx->ev_main, s));
+        CK(cudaStreamWaitEvent(sb, ctx->ev_main, 0));
+      }
+      rc = op.fn(sb);
+      CK(cudaEventRecord(ctx->ev_branch[op.branch], sb));
+      used[op.branch] = true;
+    }
+    if (rc) { if (ctx->err.empty()) ctx->err = "plan op failed"; return rc; }
+  }
+  for (int b = 1; b < 3; ++b)
+    if (used[b]) CK(cudaStreamWaitEvent(s, ctx->ev_branch[b], 0));      // join: the final kernel reads the output pyramid
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ctx->err = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
   return 0;
@@ -691,14 +735,14 @@ int run_ops(flowse_ctx* ctx, cudaStream_t s) {
 // themselves even when a per-evaluation graph exists (used while a whole sampler call is being captured).
 int run_backbone(flowse_ctx* ctx, cudaStream_t s, bool inline_ops = false) {
   Plan* p = ctx->plan.get();
-  if (inline_ops) return run_ops(ctx, s);
+  if (inline_ops) return run_ops(ctx, s, ctx->fork_branches != 0);      // s is being captured by the caller
   if (ctx->use_graph && p->eager_runs >= 1) {
     if (!p->graph_ready) {
       cudaGraph_t g = nullptr;
       if (!ctx->cap_stream) CK(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
       CK(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
       const long long c0 = launch_counter();
-      const int rc = run_ops(ctx, ctx->cap_stream);
+      const int rc = run_ops(ctx, ctx->cap_stream, ctx->fork_branches != 0);
       p->kernels_per_forward = static_cast<int>(launch_counter() - c0);
       ctx->counter_base += p->kernels_per_forward;    // captured, not executed
       cudaError_t e = cudaStreamEndCapture(ctx->cap_stream, &g);
@@ -763,6 +807,7 @@ int flowse_create(flowse_ctx** out, int device) {
   // A/B switches for measurements (the options of flowse_set_option, preset from the environment)
   if (const char* e = getenv("FLOWSE_FUSE_PREP")) ctx->fuse_prep = atoi(e);
   if (const char* e = getenv("FLOWSE_WHOLE_GRAPH")) ctx->whole_graph = atoi(e);
+  if (const char* e = getenv("FLOWSE_FORK")) ctx->fork_branches = atoi(e);
   cudaSetDevice(device);
   if (cudaMalloc(reinterpret_cast<void**>(&ctx->overflow), sizeof(unsigned long long)) != cudaSuccess ||
       cudaMemset(ctx->overflow, 0, sizeof(unsigned long long)) != cudaSuccess) {
@@ -784,6 +829,9 @@ void flowse_destroy(flowse_ctx* ctx) {
   if (ctx->arena) cudaFree(ctx->arena);
   for (auto& p : ctx->dev_allocs) cudaFree(p.first);
   if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
+  for (auto& st : ctx->side) if (st) cudaStreamDestroy(st);
+  if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
+  for (auto& ev : ctx->ev_branch) if (ev) cudaEventDestroy(ev);
   if (ctx->op_stats) cudaFree(ctx->op_stats);
   if (ctx->op_partials) cudaFree(ctx->op_partials);
   if (ctx->op_counters) cudaFree(ctx->op_counters);
@@ -1165,6 +1213,7 @@ int flowse_set_option(flowse_ctx* ctx, const char* key, int value) {
   else if (k == "graph") ctx->use_graph = value;
   else if (k == "pdl") pdl_mode() = static_cast<int>(value);
   else if (k == "whole_graph") ctx->whole_graph = value;
+  else if (k == "fork") ctx->fork_branches = value;
   else { ctx->err = "unknown option '" + k + "'"; return 2; }
   if (ctx->plan) {   // captured graphs bake the old setting
     cudaSetDevice(ctx->device);
