@@ -204,6 +204,8 @@ struct flowse_ctx {
   // cost up to hundreds of milliseconds in the bucketed evaluate driver)
   char* arena = nullptr; size_t arena_cap = 0;
   float* stft_basis = nullptr;
+  int stft_window = 0, stft_window_built = -1;   // 0 hann, 1 sqrthann (data_module.py:13-19)
+  int spec_transform = 0;                        // 0 exponent, 1 log, 2 none (data_module.py:149-175)
   char* stft_scratch = nullptr; size_t stft_scratch_bytes = 0;
   // sticky fp16 range flag: operand-producing kernels count the values whose magnitude exceeds the fp16 hi/lo range
   // (|v| > 65504 saturates silently otherwise); read back through flowse_fp16_overflow
@@ -1214,6 +1216,15 @@ int flowse_set_option(flowse_ctx* ctx, const char* key, int value) {
   else if (k == "pdl") pdl_mode() = static_cast<int>(value);
   else if (k == "whole_graph") ctx->whole_graph = value;
   else if (k == "fork") ctx->fork_branches = value;
+  else if (k == "stft_window") {
+    if (value < 0 || value > 1) { ctx->err = "stft_window: 0 (hann) or 1 (sqrthann)"; return 2; }
+    ctx->stft_window = value;   // the bases are rebuilt on the next STFT call
+    return 0;
+  } else if (k == "spec_transform") {
+    if (value < 0 || value > 2) { ctx->err = "spec_transform: 0 (exponent), 1 (log) or 2 (none)"; return 2; }
+    ctx->spec_transform = value;
+    return 0;
+  }
   else { ctx->err = "unknown option '" + k + "'"; return 2; }
   if (ctx->plan) {   // captured graphs bake the old setting
     cudaSetDevice(ctx->device);
@@ -1327,10 +1338,12 @@ int stft_prepare(flowse_ctx* ctx, const int* lengths_host, int B, int min_frames
     Lmax = std::max(Lmax, lengths_host[b]);
   }
   CK(cudaSetDevice(ctx->device));
-  if (!ctx->stft_basis) {
-    CK(cudaMalloc(reinterpret_cast<void**>(&ctx->stft_basis), stft_basis_floats() * sizeof(float)));
-    launch_stft_basis(ctx->stft_basis, s);
-    CK(cudaStreamSynchronize(s));      // built once: later calls may come on other streams
+  if (!ctx->stft_basis) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->stft_basis), stft_basis_floats() * sizeof(float)));
+  if (ctx->stft_window_built != ctx->stft_window) {
+    CK(cudaDeviceSynchronize());       // a basis of the other window may still be in use on another stream
+    launch_stft_basis(ctx->stft_basis, ctx->stft_window, s);
+    CK(cudaStreamSynchronize(s));      // built once per window: later calls may come on other streams
+    ctx->stft_window_built = ctx->stft_window;
   }
   const int Tmax = std::max(stft_frames(Lmax), min_frames);
   const long long xs = ((static_cast<long long>(Lmax) + 510 + 128 + 127) / 128) * 128;
@@ -1366,8 +1379,8 @@ int flowse_stft_spec(flowse_ctx* ctx, const float* wav, long long wav_stride, co
   if (normalize && !peak_out) { ctx->err = "stft_spec: normalize needs peak_out"; return 2; }
   if (!(spec_factor > 0.f) || !(abs_exponent > 0.f)) { ctx->err = "stft_spec: spec_factor and abs_exponent must be > 0"; return 2; }
   // the peaks are accumulated as bit patterns directly in the caller's buffer
-  launch_stft_spec(ctx->stft_basis, wav, wav_stride, sc.lengths, B, Lmax, normalize != 0, spec_factor, abs_exponent, sc.xpad,
-                   sc.xpad_stride, sc.S, reinterpret_cast<unsigned*>(peak_out), static_cast<float2*>(Y), Tpad, s);
+  launch_stft_spec(ctx->stft_basis, wav, wav_stride, sc.lengths, B, Lmax, normalize != 0, spec_factor, abs_exponent,
+                   ctx->spec_transform, sc.xpad, sc.xpad_stride, sc.S, reinterpret_cast<unsigned*>(peak_out), static_cast<float2*>(Y), Tpad, s);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1382,8 +1395,8 @@ int flowse_spec_istft(flowse_ctx* ctx, const void* X, int Tpad, const int* lengt
   if (!X || !wav_out || wav_stride < Lmax) { ctx->err = "spec_istft: null pointer or wav_stride < longest utterance"; return 2; }
   if (Tpad < stft_frames(Lmax)) { ctx->err = "spec_istft: Tpad is smaller than the frame count of the longest utterance"; return 2; }
   if (!(spec_factor > 0.f) || !(abs_exponent > 0.f)) { ctx->err = "spec_istft: spec_factor and abs_exponent must be > 0"; return 2; }
-  launch_spec_istft(ctx->stft_basis, static_cast<const float2*>(X), Tpad, sc.lengths, B, Lmax, spec_factor, abs_exponent, peak,
-                    sc.S, sc.frames, wav_out, wav_stride, s);
+  launch_spec_istft(ctx->stft_basis, static_cast<const float2*>(X), Tpad, sc.lengths, B, Lmax, spec_factor, abs_exponent,
+                    ctx->spec_transform, peak, sc.S, sc.frames, wav_out, wav_stride, s);
   CK(cudaGetLastError());
   return 0;
 }

@@ -245,16 +245,17 @@ int launch_attention(const AttentionArgs& a, cudaStream_t s, std::string* err);
 // Batched STFT / iSTFT + amplitude compression (stft.cu); n_fft 510, hop 128, hann, center=True
 // ---------------------------------------------------------------------------------------------
 size_t stft_basis_floats();                       // forward basis [510][512] + inverse basis [512][512] + window [512]
-void launch_stft_basis(float* basis, cudaStream_t s);
+void launch_stft_basis(float* basis, int sqrt_window, cudaStream_t s);
 int stft_frames(int L);                           // 1 + L / 128
+// mode: transform_type 0 exponent, 1 log, 2 none (data_module.py:149-175)
 // wav [B][wav_stride] -> Y complex [B][256][Tpad]; scratch: xpad [B][xpad_stride] (xpad_stride >= Lmax + 510 + 128,
 // multiple of 4), S complex [B][frames(Lmax)][256], peak_bits [B] (the peaks as fp32 bit patterns when normalize)
 void launch_stft_spec(const float* basis, const float* wav, long long wav_stride, const int* lengths_dev, int B, int Lmax,
-                      bool normalize, float factor, float expo, float* xpad, long long xpad_stride, float2* S,
-                      unsigned* peak_bits, float2* Y, int Tpad, cudaStream_t s);
+                      bool normalize, float factor, float expo, int mode, float* xpad, long long xpad_stride,
+                      float2* S, unsigned* peak_bits, float2* Y, int Tpad, cudaStream_t s);
 // X complex [B][256][Tpad] -> wav_out [B][wav_stride] (zeros beyond each length); scratch S as above, frames [B][T][512]
 void launch_spec_istft(const float* basis, const float2* X, int Tpad, const int* lengths_dev, int B, int Lmax, float factor,
-                       float expo, const float* peak, float2* S, float* frames, float* wav_out, long long wav_stride,
+                       float expo, int mode, const float* peak, float2* S, float* frames, float* wav_out, long long wav_stride,
                        cudaStream_t s);
 
 }  // namespace flowse

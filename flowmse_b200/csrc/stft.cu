@@ -23,23 +23,29 @@ namespace {
 
 constexpr int kNfft = 510, kHop = 128, kBins = 256, kPad = kNfft / 2;   // center=True pads n_fft/2 = 255 on both sides
 constexpr double kTwoPi = 6.283185307179586476925286766559;
+constexpr int kSpecExponent = 0, kSpecLog = 1, kSpecNone = 2;   // transform_type (data_module.py:149-175)
 
 // hann(510, periodic) in fp32, exactly torch.hann_window's formula evaluated in double and rounded
 __device__ __forceinline__ float hann(int n) {
   return static_cast<float>(0.5 - 0.5 * cos(kTwoPi * n / kNfft));
 }
+// get_window (data_module.py:13-19): 'hann' or 'sqrthann' = torch.sqrt of the fp32 hann window
+__device__ __forceinline__ float window_at(int n, int sqrt_window) {
+  const float h = hann(n);
+  return sqrt_window ? sqrtf(h) : h;
+}
 
 // fwd [510][512]: column 2f = w[k] cos(2 pi f k / 510), column 2f+1 = -w[k] sin(...)
 // inv [512][512]: row 2f = a_f w[n] cos(2 pi f n / 510) / 510, row 2f+1 = -a_f w[n] sin(...) / 510, columns >= 510 zero;
 //                 a_f = 1 for DC and Nyquist (f = 0, 255), else 2 (onesided C2R)
-__global__ void stft_basis_kernel(float* __restrict__ fwd, float* __restrict__ inv, float* __restrict__ win) {
+__global__ void stft_basis_kernel(float* __restrict__ fwd, float* __restrict__ inv, float* __restrict__ win, int sqrt_window) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < kNfft) win[i] = hann(i);
+  if (i < kNfft) win[i] = window_at(i, sqrt_window);
   if (i < kNfft * 512) {
     const int k = i / 512, col = i % 512, f = col >> 1;
     const int m = (f * k) % kNfft;                       // exact argument reduction
     const double ang = kTwoPi * m / kNfft;
-    const double w = static_cast<double>(hann(k));
+    const double w = static_cast<double>(window_at(k, sqrt_window));
     fwd[i] = static_cast<float>((col & 1) ? -w * sin(ang) : w * cos(ang));
   }
   if (i < 512 * 512) {
@@ -49,7 +55,7 @@ __global__ void stft_basis_kernel(float* __restrict__ fwd, float* __restrict__ i
       const int m = (f * n) % kNfft;
       const double ang = kTwoPi * m / kNfft;
       const double a = (f == 0 || f == kBins - 1) ? 1.0 : 2.0;
-      const double w = static_cast<double>(hann(n));
+      const double w = static_cast<double>(window_at(n, sqrt_window));
       v = static_cast<float>(((row & 1) ? -a * w * sin(ang) : a * w * cos(ang)) / kNfft);
     }
     inv[i] = v;
@@ -87,7 +93,7 @@ wav_prep_kernel(const float* __restrict__ wav, long long wav_stride, const int* 
 // frames t >= frames(b) are the zero padding of pad_spec.  32 x 32 tiles through shared memory (both sides coalesced).
 __global__ void __launch_bounds__(256)
 spec_fwd_kernel(const float2* __restrict__ S, int Tmax, const int* __restrict__ lengths, const unsigned* __restrict__ peak_bits,
-                float factor, float expo, float2* __restrict__ Y, int Tpad) {
+                float factor, float expo, int mode, float2* __restrict__ Y, int Tpad) {
   __shared__ float2 tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
@@ -108,9 +114,12 @@ spec_fwd_kernel(const float2* __restrict__ S, int Tmax, const int* __restrict__ 
     v.x *= inv_peak; v.y *= inv_peak;
     const float mag = sqrtf(v.x * v.x + v.y * v.y);
     float2 o = make_float2(0.f, 0.f);
-    if (mag > 0.f) {
-      // |X|^e * X / |X|
-      const float g = (expo == 0.5f ? sqrtf(mag) : (expo == 1.0f ? mag : powf(mag, expo))) / mag * factor;
+    if (mode == kSpecNone) {
+      o = v;
+    } else if (mag > 0.f) {
+      // exponent: |X|^e * X / |X| * factor;  log: log(1 + |X|) * X / |X| * factor
+      const float c = mode == kSpecLog ? log1pf(mag) : (expo == 0.5f ? sqrtf(mag) : (expo == 1.0f ? mag : powf(mag, expo)));
+      const float g = c / mag * factor;
       o.x = v.x * g; o.y = v.y * g;
     }
     Y[(static_cast<size_t>(b) * kBins + f0 + r) * Tpad + t] = o;
@@ -119,12 +128,13 @@ spec_fwd_kernel(const float2* __restrict__ S, int Tmax, const int* __restrict__ 
 
 // X [B][256][Tpad] complex -> S [B][Tmax][256] complex (time-major, GEMM operand): / factor, |X|^(1/e) e^{j angle}
 __global__ void __launch_bounds__(256)
-spec_back_kernel(const float2* __restrict__ X, int Tpad, float factor, float expo, float2* __restrict__ S, int Tmax) {
+spec_back_kernel(const float2* __restrict__ X, int Tpad, float factor, float expo, int mode, float2* __restrict__ S,
+                 int Tmax) {
   __shared__ float2 tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const float inv_factor = 1.0f / factor;
+  const float inv_factor = mode == kSpecNone ? 1.0f : 1.0f / factor;
   for (int r = ty; r < 32; r += 8) {
     const int t = t0 + tx;
     float2 o = make_float2(0.f, 0.f);
@@ -132,8 +142,11 @@ spec_back_kernel(const float2* __restrict__ X, int Tpad, float factor, float exp
       float2 v = X[(static_cast<size_t>(b) * kBins + f0 + r) * Tpad + t];
       v.x *= inv_factor; v.y *= inv_factor;
       const float mag = sqrtf(v.x * v.x + v.y * v.y);
-      if (mag > 0.f) {
-        const float g = (expo == 0.5f ? mag * mag : (expo == 1.0f ? mag : powf(mag, 1.0f / expo))) / mag;
+      if (mode == kSpecNone) {
+        o = v;
+      } else if (mag > 0.f) {
+        const float c = mode == kSpecLog ? expm1f(mag) : (expo == 0.5f ? mag * mag : (expo == 1.0f ? mag : powf(mag, 1.0f / expo)));
+        const float g = c / mag;
         o.x = v.x * g; o.y = v.y * g;
       }
     }
@@ -182,15 +195,15 @@ ola_kernel(const float* __restrict__ frames, int Tmax, const int* __restrict__ l
 
 size_t stft_basis_floats() { return static_cast<size_t>(kNfft) * 512 + 512 * 512 + 512; }
 
-void launch_stft_basis(float* basis, cudaStream_t s) {
+void launch_stft_basis(float* basis, int sqrt_window, cudaStream_t s) {
   float* fwd = basis; float* inv = fwd + static_cast<size_t>(kNfft) * 512; float* win = inv + 512 * 512;
-  launch_k(stft_basis_kernel, dim3((512 * 512 + 255) / 256), dim3(256), 0, s, fwd, inv, win);
+  launch_k(stft_basis_kernel, dim3((512 * 512 + 255) / 256), dim3(256), 0, s, fwd, inv, win, sqrt_window);
 }
 
 int stft_frames(int L) { return 1 + L / kHop; }
 
 void launch_stft_spec(const float* basis, const float* wav, long long wav_stride, const int* lengths_dev, int B, int Lmax,
-                      bool normalize, float factor, float expo, float* xpad, long long xpad_stride, float2* S,
+                      bool normalize, float factor, float expo, int mode, float* xpad, long long xpad_stride, float2* S,
                       unsigned* peak_bits, float2* Y, int Tpad, cudaStream_t s) {
   const int Tmax = stft_frames(Lmax);
   if (normalize) cudaMemsetAsync(peak_bits, 0, sizeof(unsigned) * B, s);
@@ -204,17 +217,17 @@ void launch_stft_spec(const float* basis, const float* wav, long long wav_stride
   launch_sgemm(g, s);
   launch_k(spec_fwd_kernel, dim3((Tpad + 31) / 32, kBins / 32, B), dim3(256), 0, s, static_cast<const float2*>(S), Tmax,
            lengths_dev, normalize ? static_cast<const unsigned*>(peak_bits) : static_cast<const unsigned*>(nullptr), factor,
-           expo, Y, Tpad);
+           expo, mode, Y, Tpad);
 }
 
 void launch_spec_istft(const float* basis, const float2* X, int Tpad, const int* lengths_dev, int B, int Lmax, float factor,
-                       float expo, const float* peak, float2* S, float* frames, float* wav_out, long long wav_stride,
+                       float expo, int mode, const float* peak, float2* S, float* frames, float* wav_out, long long wav_stride,
                        cudaStream_t s) {
   (void)Lmax;
   const int Tmax = Tpad;                              // every frame of the padded spectrogram is synthesised
   const float* inv = basis + static_cast<size_t>(kNfft) * 512;
   const float* win = inv + 512 * 512;
-  launch_k(spec_back_kernel, dim3((Tmax + 31) / 32, kBins / 32, B), dim3(256), 0, s, X, Tpad, factor, expo, S, Tmax);
+  launch_k(spec_back_kernel, dim3((Tmax + 31) / 32, kBins / 32, B), dim3(256), 0, s, X, Tpad, factor, expo, mode, S, Tmax);
   SgemmArgs g{};
   g.A = reinterpret_cast<const float*>(S); g.lda = 512; g.strideA = static_cast<long long>(Tmax) * 512;
   g.Bm = inv; g.ldb = 512; g.strideB = 0; g.transB = 0;

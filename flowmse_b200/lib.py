@@ -254,11 +254,28 @@ class Context:
         """Frames torch.stft(center=True, hop 128) yields for `length` samples (data_module.py:163-170)."""
         return 1 + int(length) // 128
 
+    _TRANSFORMS = {"exponent": 0, "log": 1, "none": 2}
+    _WINDOWS = {"hann": 0, "sqrthann": 1}
+
+    def _stft_mode(self, transform_type: str, window: str):
+        """Select the amplitude transform (data_module.py:149-175) and the STFT window (data_module.py:13-19)."""
+        if transform_type not in self._TRANSFORMS:
+            raise ValueError(f"transform_type must be one of {sorted(self._TRANSFORMS)}")
+        if window not in self._WINDOWS:
+            raise NotImplementedError(f"Window type {window} not implemented!")
+        mode = (self._TRANSFORMS[transform_type], self._WINDOWS[window])
+        if getattr(self, "_stft_mode_set", None) != mode:
+            self.set_option("spec_transform", mode[0])
+            self.set_option("stft_window", mode[1])
+            self._stft_mode_set = mode
+
     def stft_spec(self, wav: torch.Tensor, lengths, normalize: bool = True, spec_factor: float = 0.15,
-                  abs_exponent: float = 0.5, Tpad: Optional[int] = None):
+                  abs_exponent: float = 0.5, Tpad: Optional[int] = None, transform_type: str = "exponent",
+                  window: str = "hann"):
         """wav: fp32 CUDA [B, Lmax] (rows zero-padded to the longest utterance), lengths: samples per utterance.
         Returns (Y complex64 [B,1,256,Tpad], peak fp32 [B]) - the padded model-domain spectrograms evaluate.py:107-115
         builds per file, for the whole ragged batch at once."""
+        self._stft_mode(transform_type, window)
         if wav.dtype != torch.float32 or not wav.is_cuda or wav.dim() != 2 or not wav.is_contiguous():
             raise ValueError("wav must be a contiguous fp32 CUDA tensor [B, Lmax]")
         B = wav.shape[0]
@@ -277,8 +294,9 @@ class Context:
         return Y, peak
 
     def spec_istft(self, X: torch.Tensor, lengths, peak: Optional[torch.Tensor] = None, spec_factor: float = 0.15,
-                   abs_exponent: float = 0.5) -> torch.Tensor:
+                   abs_exponent: float = 0.5, transform_type: str = "exponent", window: str = "hann") -> torch.Tensor:
         """X: complex64 CUDA [B,1,256,Tpad] -> fp32 [B, max(lengths)] waveforms (VFModel.to_audio per row, times peak)."""
+        self._stft_mode(transform_type, window)
         if X.dtype != torch.complex64 or not X.is_cuda or X.dim() != 4 or not X.is_contiguous():
             raise ValueError("X must be a contiguous complex64 CUDA tensor [B,1,256,Tpad]")
         B, Tpad = X.shape[0], X.shape[3]

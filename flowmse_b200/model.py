@@ -220,8 +220,10 @@ class VFModel(nn.Module):
 
     def _device_stft_ok(self):
         dm = self.data_module
-        # the device STFT kernels are specialised to the FlowSE defaults; anything else takes the per-file torch path
-        return (dm.n_fft == 510 and dm.hop_length == 128 and dm.transform_type == "exponent" and dm.window == "hann")
+        # the device STFT kernels are specialised to the frame geometry the backbone needs (n_fft 510 -> F = 256, hop
+        # 128); every transform_type and window of the reference is handled on the device
+        return (dm.n_fft == 510 and dm.hop_length == 128 and dm.transform_type in ("exponent", "log", "none")
+                and dm.window in ("hann", "sqrthann"))
 
     def enhance_batch(self, wavs, N=5, odesolver="euler", normalize=True, **kw):
         """evaluate.py:97-136 for a list of 1-D waveforms of ANY lengths on one CUDA device, without the per-file host
@@ -249,10 +251,12 @@ class VFModel(nn.Module):
             for r, i in enumerate(idx):
                 wav[r, :lens[i]] = wavs[i].reshape(-1).to(device=dev, dtype=torch.float32)
             Y, peak = ctx.stft_spec(wav, Lb, normalize=normalize, spec_factor=dm.spec_factor,
-                                    abs_exponent=dm.spec_abs_exponent, Tpad=Tpad)
+                                    abs_exponent=dm.spec_abs_exponent, Tpad=Tpad, transform_type=dm.transform_type,
+                                    window=dm.window)
             X = self.enhance_spec(Y, N=N, odesolver=odesolver, **kw)
             x_hat = ctx.spec_istft(X.contiguous(), Lb, peak=peak if normalize else None, spec_factor=dm.spec_factor,
-                                   abs_exponent=dm.spec_abs_exponent)
+                                   abs_exponent=dm.spec_abs_exponent, transform_type=dm.transform_type,
+                                   window=dm.window)
             for r, i in enumerate(idx):
                 out[i] = x_hat[r, :lens[i]]
         return out

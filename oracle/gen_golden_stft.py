@@ -47,7 +47,29 @@ def main():
         out[f"X_{name}"] = torch.view_as_real(X).numpy()
         out[f"xhat_{name}"] = x_hat.numpy()
         print(name, "wav", tuple(wav.shape), "Y", tuple(Y.shape), "->", tuple(Yp.shape), "x_hat", tuple(x_hat.shape))
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "stft_roundtrip.npz"), **out)
+    if "--variants-only" not in sys.argv:
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "stft_roundtrip.npz"), **out)
+
+    # the non-default transform_type / window choices of SpecsDataModule (data_module.py:13-19, 149-175), one short
+    # utterance each -> tests/golden/stft_variants.npz
+    var = {}
+    n = 5003
+    g = torch.Generator().manual_seed(2)
+    tg = torch.arange(n) / 16000.0
+    wav = 0.2 * torch.randn(1, n, generator=g) + 0.5 * torch.sin(2 * np.pi * 440 * tg)
+    norm = wav.abs().max()
+    var["wav"] = wav.numpy()
+    var["norm"] = np.array([norm.item()], dtype=np.float32)
+    for transform_type, window in (("log", "hann"), ("exponent", "sqrthann"), ("none", "sqrthann"), ("log", "sqrthann")):
+        dmv = SpecsDataModule(base_dir="", transform_type=transform_type, window=window)
+        Yp = pad_spec(torch.unsqueeze(dmv.spec_fwd(dmv.stft(wav / norm)), 0))
+        X = Yp * (0.8 + 0.2j)
+        x_hat = dmv.istft(dmv.spec_back(X.squeeze()), n) * norm
+        key = f"{transform_type}_{window}"
+        var[f"Y_{key}"] = torch.view_as_real(Yp).numpy()
+        var[f"xhat_{key}"] = x_hat.numpy()
+        print(key, "Y", tuple(Yp.shape), "max|Y|", Yp.abs().max().item(), "max|x_hat|", x_hat.abs().max().item())
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "stft_variants.npz"), **var)
 
 
 if __name__ == "__main__":

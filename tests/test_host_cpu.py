@@ -214,6 +214,24 @@ def test_config1_stft_plumbing_matches_reference_golden(golden_dir):
     assert torch.allclose(back, wav, atol=2e-4)
 
 
+@pytest.mark.parametrize("transform_type,window", [("log", "hann"), ("exponent", "sqrthann"), ("none", "sqrthann")])
+def test_spec_transform_variants_match_reference_golden(golden_dir, transform_type, window):
+    """The torch mirror of SpecsDataModule's other transform_type / window settings (data_module.py:13-19, 149-175)
+    against vectors from the reference (oracle/gen_golden_stft.py -> stft_variants.npz)."""
+    from flowmse_b200.model import SpecTransform
+    from flowmse_b200.util.other import pad_spec
+    g = np.load(os.path.join(golden_dir, "stft_variants.npz"))
+    key = f"{transform_type}_{window}"
+    wav = torch.from_numpy(g["wav"])
+    norm = torch.from_numpy(g["norm"])
+    st = SpecTransform(transform_type=transform_type, window=window)
+    Yp = pad_spec(torch.unsqueeze(st.spec_fwd(st.stft(wav / norm)), 0))
+    Yg = torch.view_as_complex(torch.from_numpy(g[f"Y_{key}"]).contiguous())
+    assert torch.allclose(torch.view_as_real(Yp), torch.view_as_real(Yg), rtol=1e-5, atol=1e-6)
+    x_hat = st.istft(st.spec_back((Yg * (0.8 + 0.2j)).squeeze()), wav.shape[1]) * norm
+    assert torch.allclose(x_hat, torch.from_numpy(g[f"xhat_{key}"]), rtol=1e-5, atol=1e-6)
+
+
 # ---- evaluate driver (SURVEY.md 8f N2): host logic ---------------------------------------------------------------
 def test_evaluate_cli_matches_reference_arguments():
     """Same argument names / defaults as /root/reference/evaluate.py:27-43."""
