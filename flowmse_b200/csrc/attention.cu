@@ -7,7 +7,9 @@
 //
 // 1.63 GFLOP per network evaluation (0.15 % of the FLOPs): exact fp32 SIMT FMAs, no tensor cores.  What the old path
 // (four GEMM launches + a softmax kernel + a prep kernel, scores round-tripping through global memory) paid for was
-// launches and latency; here a CTA owns R = 8 tokens (query rows) and keeps everything of those rows on chip.
+// launches and latency; here a CTA owns R tokens (query rows; R = 8, 4 or 2, the largest that still gives the grid about
+// one CTA per SM - both kernels are FMA-issue bound, so at B = 1 halving R halves the time) and keeps everything of those
+// rows on chip.
 //
 // Data movement is arranged so that NO operand tile is staged in shared memory:
 //   * the per-CTA operands that every thread needs (the 8 normalised rows, the 8 query rows, the 8 probability rows, the
@@ -27,7 +29,7 @@ namespace flowse {
 namespace {
 
 constexpr int kC = 256;          // channels of every attention block of the default config
-constexpr int kR = 8;            // tokens (query rows) per CTA
+constexpr int kRMax = 8;         // most tokens (query rows) per CTA
 constexpr int kThreads = 256;
 constexpr int kStreamU = 16;     // 16-byte loads per thread and batch of the streaming loops (2 batches in flight)
 
@@ -42,31 +44,44 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// acc[r][0..3] += h[r] * w for the 8 rows of a CTA; h0 / h1 hold rows 0-3 / 4-7 of one shared-memory operand column
-__device__ __forceinline__ void fma_rows(float (&acc)[kR][4], const float4 h0, const float4 h1, const float4 w) {
-  const float h[kR] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+// acc[r][0..3] += h[r] * w for the R rows of a CTA; col points at the R row values of one shared-memory operand column
+template <int R>
+__device__ __forceinline__ void fma_rows(float (&acc)[R][4], const float* col, const float4 w) {
+  float h[R];
+  if constexpr (R == 8) {
+    const float4 h0 = *reinterpret_cast<const float4*>(col), h1 = *reinterpret_cast<const float4*>(col + 4);
+    h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+  } else if constexpr (R == 4) {
+    const float4 h0 = *reinterpret_cast<const float4*>(col);
+    h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w;
+  } else {
+    static_assert(R == 2, "R in {8, 4, 2}");
+    const float2 h0 = *reinterpret_cast<const float2*>(col);
+    h[0] = h0.x; h[1] = h0.y;
+  }
 #pragma unroll
-  for (int r = 0; r < kR; ++r) {
+  for (int r = 0; r < R; ++r) {
     acc[r][0] = fmaf(h[r], w.x, acc[r][0]); acc[r][1] = fmaf(h[r], w.y, acc[r][1]);
     acc[r][2] = fmaf(h[r], w.z, acc[r][2]); acc[r][3] = fmaf(h[r], w.w, acc[r][3]);
   }
 }
 
-// The streaming loop all four GEMM phases share: acc[8][4] += sum_i colT[i0 + i*istep][0..7] (x) g[i0 + i*istep][0..3] for
+// The streaming loop all four GEMM phases share: acc[R][4] += sum_i colT[i0 + i*istep][0..R-1] (x) g[i0 + i*istep][0..3] for
 // i < n.  `g` rows are `gstride` floats apart in global memory (this thread's 4 contiguous floats), `colT` is the
-// [index][8 rows] shared-memory operand.  U rows are requested one batch ahead of the batch being consumed, so 2U 16-byte
+// [index][R rows] shared-memory operand.  U rows are requested one batch ahead of the batch being consumed, so 2U 16-byte
 // loads per thread are in flight: with 256 threads that is 64 KB per SM, enough to cover the L2 latency at full rate
 // (the first version waited for every batch and ran 20x slower than its FMA count).
-template <int U>
-__device__ __forceinline__ void stream_fma(float (&acc)[kR][4], const float* __restrict__ g, size_t gstride,
+template <int U, int R>
+__device__ __forceinline__ void stream_fma(float (&acc)[R][4], const float* __restrict__ g, size_t gstride,
                                            const float* __restrict__ colT, int i0, int istep, int n, bool live) {
+  if (!live) return;                     // a thread outside the operand contributes nothing (its accumulators stay 0)
   float4 cur[U], nxt[U];
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   auto load = [&](float4 (&dst)[U], int base) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int i = base + u;
-      dst[u] = (live && i < n) ? __ldg(reinterpret_cast<const float4*>(g + static_cast<size_t>(i0 + i * istep) * gstride)) : zero;
+      dst[u] = (i < n) ? __ldg(reinterpret_cast<const float4*>(g + static_cast<size_t>(i0 + i * istep) * gstride)) : zero;
     }
   };
   auto consume = [&](const float4 (&src)[U], int base) {
@@ -74,8 +89,7 @@ __device__ __forceinline__ void stream_fma(float (&acc)[kR][4], const float* __r
     for (int u = 0; u < U; ++u) {
       const int i = base + u;
       if (i < n) {
-        const float* col = colT + static_cast<size_t>(i0 + i * istep) * kR;
-        fma_rows(acc, *reinterpret_cast<const float4*>(col), *reinterpret_cast<const float4*>(col + 4), src[u]);
+        fma_rows<R>(acc, colT + static_cast<size_t>(i0 + i * istep) * R, src[u]);
       }
     }
   };
@@ -103,8 +117,9 @@ struct QkvK {
 
 constexpr int kQkvThreads = 384;      // 192 column quads of [q | k | v] x 2 halves of the input channels
 
-// grid (ceil(L / 8), B): thread (cq, half) owns output columns 4cq .. 4cq+3 of the 768 for the CTA's 8 tokens and sums the
+// grid (ceil(L / R), B): thread (cq, half) owns output columns 4cq .. 4cq+3 of the 768 for the CTA's R tokens and sums the
 // input channels of its half; the two halves are folded through shared memory.
+template <int kR>
 __global__ void __launch_bounds__(kQkvThreads)
 attn_qkv_kernel(const QkvK k) {
   __shared__ __align__(16) float hT[kC][kR];        // normalised rows, transposed
@@ -154,7 +169,7 @@ attn_qkv_kernel(const QkvK k) {
   float acc[kR][4];
 #pragma unroll
   for (int r = 0; r < kR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
-  stream_fma<kStreamU>(acc, k.wqkv + 4 * cq, 3 * kC, &hT[0][0], half * (kC / 2), 1, kC / 2, true);
+  stream_fma<kStreamU, kR>(acc, k.wqkv + 4 * cq, 3 * kC, &hT[0][0], half * (kC / 2), 1, kC / 2, true);
   if (half == 1) {
 #pragma unroll
     for (int r = 0; r < kR; ++r) *reinterpret_cast<float4*>(&red[cq][r][0]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
@@ -174,13 +189,18 @@ attn_qkv_kernel(const QkvK k) {
     for (int r = 0; r < kR; ++r)
       if (l0 + r < L) *reinterpret_cast<float4*>(dst + static_cast<size_t>(r) * kC) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
   } else {
-    // keys transposed: kT[b][n][l0 .. l0+7]
+    // keys transposed: kT[b][n][l0 .. l0+R-1]
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float* kt = k.kT + (static_cast<size_t>(b) * kC + n0 + i) * L + l0;
       if (l0 + kR <= L) {
-        *reinterpret_cast<float4*>(kt) = make_float4(acc[0][i], acc[1][i], acc[2][i], acc[3][i]);
-        *reinterpret_cast<float4*>(kt + 4) = make_float4(acc[4][i], acc[5][i], acc[6][i], acc[7][i]);
+        if constexpr (kR == 2) {
+          *reinterpret_cast<float2*>(kt) = make_float2(acc[0][i], acc[1][i]);
+        } else {
+#pragma unroll
+          for (int r4 = 0; r4 < kR; r4 += 4)
+            *reinterpret_cast<float4*>(kt + r4) = make_float4(acc[r4][i], acc[r4 + 1][i], acc[r4 + 2][i], acc[r4 + 3][i]);
+        }
       } else {
 #pragma unroll
         for (int r = 0; r < kR; ++r) if (l0 + r < L) kt[r] = acc[r][i];
@@ -202,8 +222,9 @@ struct CoreK {
 
 constexpr int kKeysPerPass = 512;      // 128 key quads x 2 channel halves = 256 threads
 
-// grid (ceil(L / 8), B), 256 threads.  Dynamic shared memory: S [8][Lpad] scores, Pt [Lpad][8] probabilities (transposed),
-// qT / oT [C][8] query rows, later the context rows, red [4][8][C] partial sums of the thread groups.
+// grid (ceil(L / R), B), 256 threads.  Dynamic shared memory: S [R][Lpad] scores, Pt [Lpad][R] probabilities (transposed),
+// qT / oT [C][R] query rows, later the context rows, red [4][R][C] partial sums of the thread groups.
+template <int kR>
 __global__ void __launch_bounds__(kThreads)
 attn_core_kernel(const CoreK k) {
   extern __shared__ __align__(16) float sm[];
@@ -233,7 +254,7 @@ attn_core_kernel(const CoreK k) {
       float acc[kR][4];
 #pragma unroll
       for (int r = 0; r < kR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
-      stream_fma<kStreamU>(acc, kTb + key, L, qT, half * (kC / 2), 1, kC / 2, live);
+      stream_fma<kStreamU, kR>(acc, kTb + key, L, qT, half * (kC / 2), 1, kC / 2, live);
       if (half == 1) {
 #pragma unroll
         for (int r = 0; r < kR; ++r)
@@ -254,7 +275,7 @@ attn_core_kernel(const CoreK k) {
   }
   __syncthreads();
   // ---- softmax over the keys: warp r owns row r (layerspp.py:84)
-  {
+  if (warp < kR) {
     const float* row = S + static_cast<size_t>(warp) * k.Lpad;
     float m = -INFINITY;
     for (int i = lane; i < L; i += 32) m = fmaxf(m, row[i]);
@@ -272,7 +293,7 @@ attn_core_kernel(const CoreK k) {
 #pragma unroll
     for (int r = 0; r < kR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
     const int nkeys = (L - grp + 3) / 4;             // keys grp, grp + 4, ... < L
-    stream_fma<kStreamU>(acc, k.v + static_cast<size_t>(b) * L * kC + 4 * cq, kC, Pt, grp, 4, nkeys, true);
+    stream_fma<kStreamU, kR>(acc, k.v + static_cast<size_t>(b) * L * kC + 4 * cq, kC, Pt, grp, 4, nkeys, true);
 #pragma unroll
     for (int r = 0; r < kR; ++r)
       *reinterpret_cast<float4*>(red + (static_cast<size_t>(grp) * kR + r) * kC + 4 * cq) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
@@ -289,7 +310,7 @@ attn_core_kernel(const CoreK k) {
     float acc[kR][4];
 #pragma unroll
     for (int r = 0; r < kR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
-    stream_fma<kStreamU>(acc, k.w3 + 4 * cq, kC, oT, grp * (kC / 4), 1, kC / 4, true);
+    stream_fma<kStreamU, kR>(acc, k.w3 + 4 * cq, kC, oT, grp * (kC / 4), 1, kC / 4, true);
     __syncthreads();                                 // everyone has read its share of red
 #pragma unroll
     for (int r = 0; r < kR; ++r)
@@ -329,22 +350,39 @@ int launch_attention(const AttentionArgs& a, cudaStream_t s, std::string* err) {
   if (a.C != kC) { if (err) *err = "attention: the kernels are specialised to 256 channels"; return 1; }
   if (a.L <= 0 || (a.L & 3)) { if (err) *err = "attention: token count must be a positive multiple of 4"; return 1; }
   const int Lpad = ((a.L + kKeysPerPass - 1) / kKeysPerPass) * kKeysPerPass;
-  const size_t smem = (static_cast<size_t>(2) * kR * Lpad + static_cast<size_t>(kC) * kR + static_cast<size_t>(4) * kR * kC) * sizeof(float);
+  // rows per CTA of the core kernel: the most that still spreads the block over about one CTA per SM (it is bound by FMA
+  // issue per CTA; measured at B = 1, L = 512: 8 rows -> 64 CTAs 59 us, 4 rows -> 128 CTAs 35.5 us; L = 32: 45 -> 15 us).
+  // Every row's arithmetic is independent of the choice, so results do not depend on the batch size.  (Staggering the
+  // CTAs' passes over the shared operands to spread them over the L2 slices gained 6 % of the attention time and cost
+  // that property: not kept.)
+  int R = kRMax;
+  while (R > 2 && static_cast<long long>((a.L + R - 1) / R) * a.B < 96) R >>= 1;
+  const size_t smem = (static_cast<size_t>(2) * R * Lpad + static_cast<size_t>(kC) * R + static_cast<size_t>(4) * R * kC) * sizeof(float);
   if (smem > 200 * 1024) { if (err) *err = "attention: too many tokens for the shared-memory score rows"; return 1; }
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(200 * 1024));
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_core_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(200 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_core_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(200 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_core_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(200 * 1024));
     if (e != cudaSuccess) { if (err) *err = std::string("attention: cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
-    attr_smem = 200 * 1024;
+    attr_set = true;
   }
   float* q = a.scratch;
   float* kT = q + static_cast<size_t>(a.B) * a.L * kC;
   float* v = kT + static_cast<size_t>(a.B) * a.L * kC;
-  dim3 grid((a.L + kR - 1) / kR, a.B);
+  // the QKV kernel streams 768 KB of weights per CTA and is bound by that, not by FMA issue: 8 rows per CTA unless the
+  // block is tiny (measured at L = 512, B = 1: 8 rows 18.7 us, 4 rows 23.4 us; L = 32: 8 rows 19.4 us, 2 rows 16.3 us)
+  const int Rq = (static_cast<long long>((a.L + kRMax - 1) / kRMax) * a.B >= 32) ? kRMax : 2;
+  dim3 grid((a.L + R - 1) / R, a.B), gridq((a.L + Rq - 1) / Rq, a.B);
   QkvK qk{a.x, a.qs, a.gamma, a.beta, a.wqkv, a.bqkv, q, kT, v, a.L};
-  launch_k(attn_qkv_kernel, grid, dim3(kQkvThreads), 0, s, qk);
   CoreK ck{a.x, q, kT, v, a.w3, a.b3, a.out, a.qstats, a.L, Lpad, 1.0f / sqrtf(static_cast<float>(kC))};
-  launch_k(attn_core_kernel, grid, dim3(kThreads), smem, s, ck);
+  if (Rq == kRMax) launch_k(attn_qkv_kernel<8>, gridq, dim3(kQkvThreads), 0, s, qk);
+  else launch_k(attn_qkv_kernel<2>, gridq, dim3(kQkvThreads), 0, s, qk);
+  switch (R) {
+    case 8: launch_k(attn_core_kernel<8>, grid, dim3(kThreads), smem, s, ck); break;
+    case 4: launch_k(attn_core_kernel<4>, grid, dim3(kThreads), smem, s, ck); break;
+    default: launch_k(attn_core_kernel<2>, grid, dim3(kThreads), smem, s, ck); break;
+  }
   return 0;
 }
 
