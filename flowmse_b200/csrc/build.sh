@@ -7,7 +7,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 mkdir -p build
 pids=()
 for f in engine conv_gemm conv_halo kernels_gn kernels_pointwise sgemm stft attention; do
-  if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ flowse_internal.h -nt build/$f.o ] || [ ptx.cuh -nt build/$f.o ] || [ operand.cuh -nt build/$f.o ] || [ ../../include/flowse.h -nt build/$f.o ]; then
+  if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ flowse_internal.h -nt build/$f.o ] || [ ptx.cuh -nt build/$f.o ] || [ operand.cuh -nt build/$f.o ] || [ prep.cuh -nt build/$f.o ] || [ ../../include/flowse.h -nt build/$f.o ]; then
     $NVCC $FLAGS ${XFLAGS} -c $f.cu -o build/$f.o &
     pids+=($!)
   fi

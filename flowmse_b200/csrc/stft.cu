@@ -23,7 +23,7 @@ namespace {
 
 constexpr int kNfft = 510, kHop = 128, kBins = 256, kPad = kNfft / 2;   // center=True pads n_fft/2 = 255 on both sides
 constexpr double kTwoPi = 6.283185307179586476925286766559;
-constexpr int kSpecExponent = 0, kSpecLog = 1, kSpecNone = 2;   // transform_type (data_module.py:149-175)
+constexpr int kSpecLog = 1, kSpecNone = 2;        // 0 = exponent;   // transform_type (data_module.py:149-175)
 
 // hann(510, periodic) in fp32, exactly torch.hann_window's formula evaluated in double and rounded
 __device__ __forceinline__ float hann(int n) {
