@@ -359,7 +359,8 @@ int launch_attention(const AttentionArgs& a, cudaStream_t s, std::string* err) {
   while (R > 2 && static_cast<long long>((a.L + R - 1) / R) * a.B < 96) R >>= 1;
   const size_t smem = (static_cast<size_t>(2) * R * Lpad + static_cast<size_t>(kC) * R + static_cast<size_t>(4) * R * kC) * sizeof(float);
   if (smem > 200 * 1024) { if (err) *err = "attention: too many tokens for the shared-memory score rows"; return 1; }
-  static bool attr_set = false;
+  static PerDevice<bool> attr_done(false);
+  bool& attr_set = attr_done.get();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_core_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(200 * 1024));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_core_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(200 * 1024));

@@ -693,7 +693,8 @@ bool check_args(const ConvGemmArgs& a, std::string* err) {
 // is not available.  Queried once per instantiation.  Clusters of up to 8 CTAs are always schedulable.
 template <int BN>
 int max_clusters16() {
-  static int cached = -1;
+  static PerDevice<int> cache(-1);
+  int& cached = cache.get();
   if (cached >= 0) return cached;
   using C = Cfg<BN>;
   cached = 0;
@@ -718,7 +719,8 @@ int max_clusters16() {
 template <int BN>
 int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   using C = Cfg<BN>;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_done(false);
+  bool& attr_set = attr_done.get();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);

@@ -763,7 +763,8 @@ int num_sms() {
 template <int BN, int NMAIN, bool PAIR, bool XF = false>
 int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   using C = HCfg<BN, NMAIN, PAIR>;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_done(false);
+  bool& attr_set = attr_done.get();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, NMAIN, PAIR, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);

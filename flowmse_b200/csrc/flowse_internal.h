@@ -12,6 +12,19 @@ namespace flowse {
 // Process-wide count of kernel launches issued by this library (incremented by every launch_* helper).
 long long& launch_counter();
 
+// Function attributes (dynamic shared-memory limit, non-portable cluster sizes) and occupancy answers belong to a DEVICE:
+// a per-launcher cache has one entry per device, indexed by the current one.
+template <class T>
+struct PerDevice {
+  T v[64];
+  explicit PerDevice(T init) { for (auto& e : v) e = init; }
+  T& get() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return v[(d >= 0 && d < 64) ? d : 0];
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL).  One NFE is a chain of ~330 mostly short kernels; every kernel of the library
 //   1. calls pdl_launch_dependents() first: the NEXT kernel of the stream / graph may be scheduled as soon as all CTAs

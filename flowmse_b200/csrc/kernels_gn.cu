@@ -412,7 +412,8 @@ void launch_head_t(const HeadK& k, cudaStream_t s) {
   constexpr int TH = RG * P, RW = TW + 2, RH = TH + 2;
   const size_t tile = std::max(static_cast<size_t>(RH) * RW * (CC + 4), static_cast<size_t>(KS) * TH * TW * 4);
   const size_t smem = (tile + 9 * CC * 4 + 2 * k.C) * sizeof(float);
-  static bool attr_set = false;
+  static PerDevice<bool> attr_done(false);
+  bool& attr_set = attr_done.get();
   if (!attr_set) {
     cudaFuncSetAttribute(head_conv_kernel<TW, RG, P, KS, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_set = true;
