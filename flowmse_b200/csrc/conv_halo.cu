@@ -808,7 +808,7 @@ int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = s;
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_mode() == 1 ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (pdl_mode() == 1 || pdl_mode() == 4) ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (PAIR) {
     const int clusters = std::min(p.num_items, num_sms() / 2);

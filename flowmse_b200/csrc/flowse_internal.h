@@ -35,7 +35,7 @@ struct PerDevice {
 // launch_k() sets cudaLaunchAttributeProgrammaticStreamSerialization in mode 1 only; the conv_gemm launches set it in
 // modes 1 and 2 (the default: measurements in pdl_mode(), kernels_pointwise.cu).
 // ---------------------------------------------------------------------------------------------
-int& pdl_mode();      // 0 off, 1 all kernels, 2 low-resolution conv_gemm launches only
+int& pdl_mode();      // 0 off, 1 all kernels, 2 low-resolution conv_gemm launches only, 3 = 2 + small grids, 4 = 2 + halo launches
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

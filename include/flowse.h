@@ -105,7 +105,8 @@ int flowse_fp16_overflow(flowse_ctx* ctx, long long* count, int reset);
 /* Options: "conv_impl" 0 = tcgen05 (default: halo kernel on high-resolution layers, per-tap kernel otherwise),
  * 1 = SIMT cross-check, 2 = per-tap kernel everywhere, 3 = like 0 with 3 rotating main accumulators in the halo kernel,
  * 4 = like 0 with the CTA-pair (cta_group::2) halo kernel; "graph" 0/1 = replay each NFE as a CUDA graph; "pdl" = programmatic dependent launch (process-wide):
- * 0 off, 1 every kernel, 2 (default) the low-resolution conv launches only - the fastest of the three under graph replay;
+ * 0 off, 1 every kernel, 2 (default) the low-resolution conv launches only - the fastest under graph replay, 3 = 2 + every
+ * launch of at most 148 CTAs, 4 = 2 + the halo conv launches (both measured neutral);
  * "whole_graph" 0/1 (default 1) = flowse_sample replays prior + all evaluations + updates as ONE graph from the second call
  * with a given schedule; "fuse_prep" = who prepares the conv operands (GroupNorm + SiLU + fp16 hi/lo split) of the
  * high-resolution layers: 0 a standalone pass per conv, 1 (default) the halo conv kernel itself, 2 = 1 + the plain
