@@ -66,6 +66,28 @@ constexpr int kXfWarps = 8;                              // transform warps of t
 constexpr int kFirstXfWarp = kFirstEpiWarp + kEpiWarps;  // warps 12..19
 constexpr int NUM_THREADS_XF = (kFirstXfWarp + kXfWarps) * 32;   // 640
 constexpr int kXfMaxC = 512;                             // channels of a fused operand (scale / shift table in smem)
+// How the transform warps read the fp32 activations.  Every byte is used once per CTA and the L1 data array is the same
+// SRAM the tensor core streams its operands from, so loads that do not allocate there looked attractive; measured (same
+// box, two runs each, ms per sampler call): ld.global.nc 20.89 / 20.93, .cg (L2 only) 21.28 / 21.35, .nc.L1::no_allocate
+// 21.13 / 21.12, .cs 20.97 / 20.81 - the 128-byte L1 lines serve the neighbouring lanes' 32-byte pieces.  Default kept.
+#ifndef XF_LDMODE
+#define XF_LDMODE 0
+#endif
+__device__ __forceinline__ float4 xf_load(const float4* g) {
+#if XF_LDMODE == 0
+  return __ldg(g);                                  // ld.global.nc: allocates in L1
+#elif XF_LDMODE == 1
+  return __ldcg(g);                                 // ld.global.cg: cached in L2 only
+#elif XF_LDMODE == 2
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(g));
+  return v;
+#else
+  return __ldcs(g);                                 // ld.global.cs: streaming (evict first)
+#endif
+}
+
 #ifndef XF_NB
 #define XF_NB 6
 #endif
@@ -495,7 +517,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i];
         if (inb) {
           const float4* g = reinterpret_cast<const float4*>(base + (static_cast<size_t>(h) * p.W + w) * ld);
-          v0[i] = __ldg(g); v1[i] = __ldg(g + 1);
+          v0[i] = xf_load(g); v1[i] = xf_load(g + 1);
         }
       }
     };

@@ -36,7 +36,7 @@ for rep in range(2):
         xh = ctx.spec_istft(X.contiguous(), lens, peak=peak)
         torch.cuda.synchronize(); t4 = time.time()
         tot["h2d"] += t1 - t0; tot["stft"] += t2 - t1; tot["sampler"] += t3 - t2; tot["istft"] += t4 - t3
-        rows.append((len(batch), Tpad, round(1e3 * (t3 - t2), 1)))
+        rows.append((len(batch), Tpad, round(1e3 * (t3 - t2), 1), "stft", round(1e3 * (t2 - t1), 1), "istft", round(1e3 * (t4 - t3), 1)))
     frames = sum(ev.padded_frames(n_samples[i]) for i in mine)
     print(("cold" if rep == 0 else "warm"), {k: round(v, 3) for k, v in tot.items()}, "frames", frames,
           "frames/s (sampler only)", round(frames / tot["sampler"]))
