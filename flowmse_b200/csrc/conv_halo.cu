@@ -88,6 +88,17 @@ __device__ __forceinline__ float4 xf_load(const float4* g) {
 #endif
 }
 
+// Experiment switches: which threads keep the clock reads around their barrier waits (the FLOWSE_CONV_DBG=1 counters).
+// Same-box runs, ms per sampler call: both kept 21.00 / 21.09 / 21.02, producer without 21.00 / 21.04 / 20.99, issuer
+// without 20.96 / 20.91 / 21.00, and every counter compiled out 21.36 / 21.31 / 21.32 against 21.02 / 20.99 / 21.05 - the
+// kernel's timing moves by +-1 % with changes of this kind, so the counters stay in.
+#ifndef HALO_DBG_PROD
+#define HALO_DBG_PROD 1
+#endif
+#ifndef HALO_DBG_MMA
+#define HALO_DBG_MMA 1
+#endif
+#define HALO_TW(on, acc, ...) do { if (on) { const long long c0_ = clock64(); __VA_ARGS__; acc += clock64() - c0_; } else { __VA_ARGS__; } } while (0)
 #ifndef XF_NB
 #define XF_NB 6
 #endif
@@ -280,7 +291,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       auto full_addr = [&](uint32_t local) { return PAIR ? ptx::map_to_cta(local, 0) : local; };
       auto issue_A = [&](int item, int c) {
         const TileCoord t = decode_tile<BN, PAIR>(p, item, rank);
-        { const long long c0 = clock64(); ptx::mbar_wait(a_empty(as), aph ^ 1u); w_pa += clock64() - c0; }
+        HALO_TW(HALO_DBG_PROD, w_pa, ptx::mbar_wait(a_empty(as), aph ^ 1u));
         const bool main = c < p.nchunk_main;
         if (XF && (main ? xf.a.s1 : xf.x.s1) != nullptr) {
           ptx::mbar_arrive(a_full(as));              // the transform warps fill this stage
@@ -311,7 +322,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int pre = ntap > 2 ? 2 : ntap - 1;       // prefetch the next halo while this chunk's taps stream
           for (int tp = 0; tp < ntap; ++tp) {
             const int kb = main ? tp * p.nchunk_main + c : 9 * p.nchunk_main + (c - p.nchunk_main);
-            { const long long c0 = clock64(); ptx::mbar_wait(b_empty(bs), bph ^ 1u); w_pb += clock64() - c0; }
+            HALO_TW(HALO_DBG_PROD, w_pb, ptx::mbar_wait(b_empty(bs), bph ^ 1u));
             if (rank == 0) ptx::mbar_expect_tx(b_full(bs), C::B_STAGE_BYTES * kCtas);
             const uint32_t bar = full_addr(b_full(bs));
             if constexpr (PAIR) {
@@ -362,7 +373,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int item = item0; item < p.num_items; item += item_stride, ++it) {
         const int buf = it % C::NBUF;
         const uint32_t use = static_cast<uint32_t>(it / C::NBUF);
-        { const long long c0 = clock64(); ptx::mbar_wait(t_empty(buf), (use & 1u) ^ 1u); w_t += clock64() - c0; }   // epilogue has drained this accumulator buffer
+        HALO_TW(HALO_DBG_MMA, w_t, ptx::mbar_wait(t_empty(buf), (use & 1u) ^ 1u));   // epilogue has drained this accumulator buffer
         ptx::tc_fence_after();
         const uint32_t acc = tmem_acc + static_cast<uint32_t>(buf * C::NSLOT * C::SLOT_COLS);
         const uint32_t d_corr = acc + static_cast<uint32_t>(NMAIN * C::SLOT_COLS);
@@ -370,9 +381,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = 0; c < nchunks; ++c) {
           const bool main = c < p.nchunk_main;
           const int ntap = main ? 9 : 1;
-          { const long long c0 = clock64(); ptx::mbar_wait(a_full(as), aph); w_a += clock64() - c0; }
+          HALO_TW(HALO_DBG_MMA, w_a, ptx::mbar_wait(a_full(as), aph));
           for (int tp = 0; tp < ntap; ++tp) {
-            { const long long c0 = clock64(); ptx::mbar_wait(b_full(bs), bph); w_b += clock64() - c0; }
+            HALO_TW(HALO_DBG_MMA, w_b, ptx::mbar_wait(b_full(bs), bph));
             ptx::tc_fence_after();
             // view of the halo for this tap: rows shifted by (dy+1) halo rows and (dx+1) pixels
             const int shift = main ? (tp / 3) * HALO_W + (tp % 3) : HALO_W + 1;
