@@ -63,8 +63,16 @@ constexpr int NUM_THREADS = 384;
 constexpr int kEpiWarps = 8;
 constexpr int kFirstEpiWarp = 4;
 constexpr int kXfWarps = 8;                              // transform warps of the XF variant
-constexpr int kFirstXfWarp = kFirstEpiWarp + kEpiWarps;  // warps 12..19
-constexpr int NUM_THREADS_XF = (kFirstXfWarp + kXfWarps) * 32;   // 640
+// Fused-operand variant: ONE epilogue warp per TMEM lane quadrant instead of two.  16 warps = 512 threads give every
+// thread 128 registers (640 threads: 102 -> 96), which the transform warps use for their loads in flight; a tile's
+// epilogue still fits behind the MMAs of the next tile.  Same-box A/B, ms per sampler call: 21.45-21.53 -> 21.19-21.42 at
+// B = 1, 143.2-143.5 -> 140.9-141.8 at B = 8.  Two alternating register sets for the transform (the loads of the batch
+// after the next one in flight) on top of it measured the same (21.26-21.36 / 141.7-142.0) and were not kept.
+#ifndef XF_EPI_WARPS
+#define XF_EPI_WARPS 4
+#endif
+constexpr int kEpiWarpsXf = XF_EPI_WARPS;
+constexpr int NUM_THREADS_XF = (kFirstEpiWarp + kEpiWarpsXf + kXfWarps) * 32;
 constexpr int kXfMaxC = 512;                             // channels of a fused operand (scale / shift table in smem)
 // How the transform warps read the fp32 activations.  Every byte is used once per CTA and the L1 data array is the same
 // SRAM the tensor core streams its operands from, so loads that do not allocate there looked attractive; measured (same
@@ -103,7 +111,7 @@ __device__ __forceinline__ float4 xf_load(const float4* g) {
 #define XF_NB 6
 #endif
 
-template <int BN, int NMAIN, bool PAIR>
+template <int BN, int NMAIN, bool PAIR, int EPW = kEpiWarps>
 struct HCfg {
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;               // weight rows staged by this CTA
   static constexpr int B_PLANE = B_ROWS * 128;
@@ -124,8 +132,8 @@ struct HCfg {
                                    : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int CH = 16;
   static constexpr int STG_STRIDE = CH + 4;
-  static constexpr int STG_BYTES = kEpiWarps * 32 * STG_STRIDE * 4;
-  static constexpr int COLS_PER_WARP = (BN >= 32) ? BN / 2 : BN;
+  static constexpr int STG_BYTES = EPW * 32 * STG_STRIDE * 4;
+  static constexpr int COLS_PER_WARP = (BN >= 32 && EPW == 8) ? BN / 2 : BN;
   static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + STG_BYTES + 1024;
 };
 
@@ -225,12 +233,13 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX,
                  const __grid_constant__ CUtensorMap tmW, const HaloParams p, const XfParams xf) {
   static_assert(!XF || (!PAIR && NMAIN == 1 && BN == 128), "the fused-operand variant exists for the default tile only");
-  using C = HCfg<BN, NMAIN, PAIR>;
+  constexpr int EPW = XF ? kEpiWarpsXf : kEpiWarps;           // epilogue warps
+  using C = HCfg<BN, NMAIN, PAIR, EPW>;
   extern __shared__ uint8_t smem_raw[];
   constexpr int NBARS = 2 * A_STAGES + 2 * C::B_STAGES + 2 * C::NBUF;
   __shared__ uint64_t bars[NBARS];
   __shared__ uint32_t tmem_slot_var;
-  __shared__ float s_qs[2][kEpiWarps][C::COLS_PER_WARP / 4 > 0 ? C::COLS_PER_WARP / 4 : 1][2];
+  __shared__ float s_qs[2][EPW][C::COLS_PER_WARP / 4 > 0 ? C::COLS_PER_WARP / 4 : 1][2];
   __shared__ __align__(16) float s_xsc[XF ? kXfMaxC : 4], s_xsh[XF ? kXfMaxC : 4];   // GroupNorm scale / shift per channel
 
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -249,11 +258,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 epilogue, 12..19 operand transform (XF).  (Putting
+  // Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 GroupNorm table (XF), 4.. epilogue (8 warps; XF: 4),
+  // then 8 operand-transform warps (XF).  (Putting
   // the MMA-issuing warp last - the issue arbiter favours high warp indices - was measured and makes no difference.)
-  constexpr int w_tma = 0, w_mma = 1, w_alloc = 2, w_epi0 = kFirstEpiWarp, w_xf0 = kFirstXfWarp;
+  constexpr int w_tma = 0, w_mma = 1, w_alloc = 2, w_epi0 = kFirstEpiWarp, w_xf0 = kFirstEpiWarp + EPW;
   const bool is_xf = XF && warp >= w_xf0;
-  const bool is_epi = warp >= w_epi0 && warp < w_epi0 + kEpiWarps;
+  const bool is_epi = warp >= w_epi0 && warp < w_epi0 + EPW;
   const int nchunks = p.nchunk_main + p.nchunk_sc;
   const int rank = PAIR ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   const int item0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -267,7 +277,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // XF: the producer thread and every transform warp arrive on each A stage
     for (int s = 0; s < A_STAGES; ++s) { ptx::mbar_init(a_full(s), XF ? 1 + kXfWarps : 1); ptx::mbar_init(a_empty(s), 1); }
     for (int s = 0; s < C::B_STAGES; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < C::NBUF; ++s) { ptx::mbar_init(t_full(s), 1); ptx::mbar_init(t_empty(s), kEpiWarps * kCtas); }
+    for (int s = 0; s < C::NBUF; ++s) { ptx::mbar_init(t_full(s), 1); ptx::mbar_init(t_empty(s), EPW * kCtas); }
     ptx::fence_mbar_init();
   }
   if (warp == w_alloc) {
@@ -599,8 +609,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.dbg && xt == 0) { p.dbg[blockIdx.x * 16 + 6] = w_xe; p.dbg[blockIdx.x * 16 + 7] = w_xp; }
     if (vmax > kHalfMax && xf.overflow) atomicAdd(xf.overflow, 1ull);
   } else if (is_epi) {
-    // ------------------------------------------------------------------ epilogue (8 warps)
-    // Two warps per TMEM lane quadrant, each owning half of the tile's columns, CH columns per pass: TMEM -> registers
+    // ------------------------------------------------------------------ epilogue (EPW warps)
+    // Two warps per TMEM lane quadrant, each owning half of the tile's columns (one warp and all columns in the fused-operand
+    // variant), CH columns per pass: TMEM -> registers
     // (slots summed in IEEE fp32) -> padded smem staging tile -> row-contiguous float4 residual loads / output stores.
     const int e = warp - kFirstEpiWarp;
     const int q = warp & 3;
@@ -730,9 +741,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (p.qstats) {
         // fold the four quadrant warps of each column half in a fixed order, then one fp64 atomic pair per quad
-        named_bar_sync(1, kEpiWarps * 32);
+        named_bar_sync(1, EPW * 32);
         constexpr int QPW = C::COLS_PER_WARP / 4;                 // quads per warp
-        constexpr int NQ = (BN >= 32 ? 2 : 1) * QPW;              // quads per tile
+        constexpr int NQ = ((BN >= 32 && EPW == 8) ? 2 : 1) * QPW;   // quads per tile
         if (etid < NQ) {
           const int hf = etid / QPW, qd = etid % QPW;
           const int n = t.n0 + hf * C::COLS_PER_WARP + qd * 4;
@@ -795,7 +806,8 @@ int num_sms() {
 
 template <int BN, int NMAIN, bool PAIR, bool XF = false>
 int launch_halo(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
-  using C = HCfg<BN, NMAIN, PAIR>;
+  constexpr int EPW = XF ? kEpiWarpsXf : kEpiWarps;           // epilogue warps
+  using C = HCfg<BN, NMAIN, PAIR, EPW>;
   static PerDevice<bool> attr_done(false);
   bool& attr_set = attr_done.get();
   if (!attr_set) {
