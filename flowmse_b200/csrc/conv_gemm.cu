@@ -20,7 +20,6 @@
 //  * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
 //    warps 2..5 = epilogue (TMEM -> registers -> bias/residual/scale -> global).
 #include "flowse_internal.h"
-#include "prep.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -88,15 +87,6 @@ struct GemmParams {
   // (ld.shared::cluster, fixed z order = the same deterministic summation as the two-pass path) and applies the
   // epilogue.  No partial planes in global memory, no second kernel.
   int cluster_s;
-  // Fused operand preparation (has_prep): before the main loop the CTAs that share an output tile - the split-K cluster,
-  // or the single CTA - run the plain GroupNorm + SiLU + fp16-split pass over the HALO REGION of their own tile, i.e. over
-  // exactly the rows their TMA loads will fetch, and meet at a cluster barrier (hardware, ~0.2 us); no grid-wide
-  // synchronisation, no co-residency requirement.  Neighbouring tiles (and the clusters of the other N tiles) write the
-  // pixels they share redundantly with identical values, which is benign, and every pixel of the image is written by its
-  // own tile's cluster, so a later conv can use the shortcut operand this pass also produces.  The weight tiles of the
-  // first stages are in flight meanwhile.  Saves a launch, its dependency gap and one dependent-load chain per conv.
-  PrepK prep;
-  int has_prep;
 };
 
 struct CtaTile { int b, h0, w0, n0; };
@@ -170,7 +160,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  auto stamp = [&](int slot) { if (p.dbg) p.dbg[static_cast<size_t>(cta_lin) * 12 + slot] = static_cast<long long>(ptx::globaltimer_ns()); };
+  auto stamp = [&](int slot) { if (p.dbg) p.dbg[static_cast<size_t>(cta_lin) * 8 + slot] = static_cast<long long>(ptx::globaltimer_ns()); };
   if (threadIdx.x == 0) stamp(0);
 
   // tile coordinates
@@ -209,44 +199,19 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const uint32_t tmem_acc = *tmem_slot_ptr;
   pdl_wait();                 // barriers, TMEM and tensor maps were set up while the previous kernel drained
   if (threadIdx.x == 0) stamp(1);
-  // barrier over the CTAs that share this output tile (fused operand preparation): the split-K cluster, or this CTA alone
-  auto tile_sync = [&]() {
-    if (p.cluster_s > 1) ptx::cluster_sync_all();
-    else asm volatile("bar.sync 2, %0;" ::"n"(NUM_THREADS) : "memory");
-  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      // With the fused preparation the weight tiles of the first stages do not depend on anything: request them, then wait
-      // for the grid-wide operand before the first activation tile.
-      const bool fused = p.has_prep != 0;
-      const int npre = fused ? min(C::STAGES, kb_end - kb_begin) : 0;
-      for (int i = 0; i < npre; ++i) {
-        const uint32_t sB_hi = smem_base + i * C::STAGE_BYTES + 2 * A_BYTES;
-        ptx::mbar_expect_tx(full_bar(i), C::STAGE_BYTES);
-        ptx::tma_load_3d(&tmW, full_bar(i), sB_hi, (kb_begin + i) * BK, n0, 0);
-        ptx::tma_load_3d(&tmW, full_bar(i), sB_hi + C::B_BYTES, (kb_begin + i) * BK, n0, 1);
-      }
-    }
-    if (p.has_prep) {                               // whole warp: the barrier instructions are warp-aligned
-      __syncwarp();
-      tile_sync();                                 // every CTA's share of the tile's operand is written and fenced
-    }
-    if (lane == 0) {
-      const bool fused = p.has_prep != 0;
-      const int npre = fused ? min(C::STAGES, kb_end - kb_begin) : 0;
-      if (fused) ptx::fence_proxy_async_all();     // generic-proxy global writes -> this thread's TMA reads
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const bool pre = kb - kb_begin < npre;     // stage armed and weights requested above
-        if (!pre) ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sA_hi = smem_base + stage * C::STAGE_BYTES;
         const uint32_t sA_lo = sA_hi + A_BYTES;
         const uint32_t sB_hi = sA_lo + A_BYTES;
         const uint32_t sB_lo = sB_hi + C::B_BYTES;
-        if (!pre) ptx::mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+        ptx::mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
         if (kb < nkb_main) {
           const int tap = kb / p.nchunk_main;
           const int ch = kb - tap * p.nchunk_main;
@@ -259,16 +224,13 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           ptx::tma_load_5d(&tmX, full_bar(stage), sA_hi, ch * BK, w0, h0, b, 0);
           ptx::tma_load_5d(&tmX, full_bar(stage), sA_lo, ch * BK, w0, h0, b, 1);
         }
-        if (!pre) {
-          ptx::tma_load_3d(&tmW, full_bar(stage), sB_hi, kb * BK, n0, 0);
-          ptx::tma_load_3d(&tmW, full_bar(stage), sB_lo, kb * BK, n0, 1);
-        }
+        ptx::tma_load_3d(&tmW, full_bar(stage), sB_hi, kb * BK, n0, 0);
+        ptx::tma_load_3d(&tmW, full_bar(stage), sB_lo, kb * BK, n0, 1);
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (p.has_prep) tile_sync();
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(BM, BN);
       int stage = 0;
@@ -308,30 +270,6 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     //          output) is a contiguous 64-byte run per row: LPR lanes cover one row's CH columns, RPI rows per pass.
     // Everything that does not depend on the accumulator (pixel offsets, bias, first residual block) is done
     // before waiting for the MMAs, i.e. overlapped with the main loop.
-    if (p.has_prep) {
-      // ---- fused operand preparation: this CTA's share of the tile's halo region, then the tile-wide barrier
-      __shared__ float s_mean[kGroups], s_rstd[kGroups];
-      const int etid = static_cast<int>(threadIdx.x) - 64;
-      auto sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-      const int S = p.cluster_s > 1 ? p.cluster_s : 1;
-      const int z = p.cluster_s > 1 ? static_cast<int>(blockIdx.z) : 0;
-      const bool halo = p.ntaps == 9;
-      const int RW = halo ? p.TW + 2 : p.TW, RH = halo ? p.TH + 2 : p.TH;
-      const int hb = halo ? h0 - 1 : h0, wb = halo ? w0 - 1 : w0;
-      const int Hh = p.H, Ww = p.W;
-      auto map = [=](int slot) {
-        const int hy = slot / RW, hx = slot - hy * RW;
-        const int h = hb + hy, w = wb + hx;
-        return (h >= 0 && h < Hh && w >= 0 && w < Ww) ? h * Ww + w : -1;
-      };
-      prep_pixels_body<4>(p.prep, etid, z, S, b, RW * RH, map, s_mean, s_rstd, sync);
-      if (threadIdx.x == 64) stamp(8);
-      ptx::fence_proxy_async_all();                  // this thread's global writes -> the TMA reads of the tile's CTAs
-      __syncwarp();
-      if (threadIdx.x == 64) stamp(9);
-      tile_sync();
-      if (threadIdx.x == 64) stamp(7);
-    }
     const int e = warp - 2;
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
     const int half = e >> 2;
@@ -663,18 +601,7 @@ GemmParams make_params(const ConvGemmArgs& a) {
   p.dbg = nullptr;
   p.ksplit = 1; p.partial = nullptr; p.partial_plane = 0; p.cluster_s = 0;
   p.qstats = a.qstats;
-  p.has_prep = 0;
   return p;
-}
-
-// PrepArgs -> the kernel-side description of a plain preparation pass (what launch_gn_prep builds for its own kernel)
-PrepK make_prep(const PrepArgs& a) {
-  PrepK k;
-  k.s1 = a.src1; k.C1 = a.C1; k.s2 = a.src2; k.C2 = a.src2 ? a.C2 : 0;
-  k.qs1 = a.qs1; k.qs2 = a.qs2; k.gamma = a.gamma; k.beta = a.beta;
-  k.H = a.H; k.W = a.W; k.Ho = a.H; k.Wo = a.W; k.mode = a.mode; k.silu = a.silu; k.B = a.B;
-  k.outA = a.outA; k.outX = a.outX; k.outF = a.outF; k.outXF = a.outXF; k.overflow = a.overflow;
-  return k;
 }
 
 bool check_args(const ConvGemmArgs& a, std::string* err) {
@@ -778,18 +705,10 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
       }
     }
   }
-  const size_t ncta = static_cast<size_t>(grid.x) * grid.y * grid.z;
-  if (a.has_prep) {
-    const int Cp = a.prep.C1 + (a.prep.src2 ? a.prep.C2 : 0);
-    // split-K through partial planes (no cluster) spreads a tile over independent CTAs: nothing to synchronise them with
-    const bool fuse = a.prep.mode == kPrepPlain && Cp % 8 == 0 && 256 % (Cp / 8) == 0 && (S == 1 || cluster_reduce) &&
-                      a.prep.H == a.H && a.prep.W == a.W && a.prep.B == a.B;
-    if (fuse) { p.prep = make_prep(a.prep); p.has_prep = 1; }
-    else launch_gn_prep(a.prep, s);
-  }
   static const bool dbg = getenv("FLOWSE_CONV_DBG") != nullptr;
   long long* dbuf = nullptr;
-  if (dbg) { cudaMalloc(&dbuf, ncta * 12 * sizeof(long long)); cudaMemset(dbuf, 0, ncta * 12 * sizeof(long long)); p.dbg = dbuf; }
+  const size_t ncta = static_cast<size_t>(grid.x) * grid.y * grid.z;
+  if (dbg) { cudaMalloc(&dbuf, ncta * 8 * sizeof(long long)); cudaMemset(dbuf, 0, ncta * 8 * sizeof(long long)); p.dbg = dbuf; }
   if (cluster_reduce) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = s;
@@ -814,26 +733,20 @@ int launch_bn(const ConvGemmArgs& a, cudaStream_t s, std::string* err) {
   }
   if (dbg) {
     cudaStreamSynchronize(s);
-    std::vector<long long> h(ncta * 12);
+    std::vector<long long> h(ncta * 8);
     cudaMemcpy(h.data(), dbuf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(dbuf);
     double ph[5] = {0, 0, 0, 0, 0};
     long long tmin = h[0], tmax = 0;
     for (size_t c = 0; c < ncta; ++c) {
-      for (int k = 0; k < 5; ++k) ph[k] += static_cast<double>(h[c * 12 + k + 1] - h[c * 12 + k]);
-      tmin = std::min(tmin, h[c * 12]); tmax = std::max(tmax, h[c * 12 + 5]);
+      for (int k = 0; k < 5; ++k) ph[k] += static_cast<double>(h[c * 8 + k + 1] - h[c * 8 + k]);
+      tmin = std::min(tmin, h[c * 8]); tmax = std::max(tmax, h[c * 8 + 5]);
     }
     double park = 0.0;
-    if (cluster_reduce) for (size_t c = 0; c < ncta; ++c) park += static_cast<double>(h[c * 12 + 6] - h[c * 12 + 3]);
-    double prep = 0.0;
-    double pbody = 0.0, pfence = 0.0;
-    if (p.has_prep) for (size_t c = 0; c < ncta; ++c) {
-      prep += static_cast<double>(h[c * 12 + 7] - h[c * 12 + 1]);
-      pbody += static_cast<double>(h[c * 12 + 8] - h[c * 12 + 1]); pfence += static_cast<double>(h[c * 12 + 9] - h[c * 12 + 8]);
-    }
-    fprintf(stderr, "[conv dbg] grid=(%u,%u,%u) kb=%d  setup %.2f us | first-data %.2f (fused prep + tile barrier %.2f: body %.2f, proxy fence %.2f) | mainloop %.2f | epilogue %.2f (park+cluster barrier %.2f) | teardown %.2f | kernel span %.2f us\n",
-            grid.x, grid.y, grid.z, p.ntaps * p.nchunk_main + p.nchunk_sc, ph[0] / ncta / 1e3, ph[1] / ncta / 1e3, prep / ncta / 1e3, pbody / ncta / 1e3, pfence / ncta / 1e3,
-            ph[2] / ncta / 1e3, ph[3] / ncta / 1e3, park / ncta / 1e3, ph[4] / ncta / 1e3, (tmax - tmin) / 1e3);
+    if (cluster_reduce) for (size_t c = 0; c < ncta; ++c) park += static_cast<double>(h[c * 8 + 6] - h[c * 8 + 3]);
+    fprintf(stderr, "[conv dbg] grid=(%u,%u,%u) kb=%d  setup %.2f us | first-data %.2f | mainloop %.2f | epilogue %.2f (park+cluster barrier %.2f) | teardown %.2f | kernel span %.2f us\n",
+            grid.x, grid.y, grid.z, p.ntaps * p.nchunk_main + p.nchunk_sc, ph[0] / ncta / 1e3, ph[1] / ncta / 1e3, ph[2] / ncta / 1e3,
+            ph[3] / ncta / 1e3, park / ncta / 1e3, ph[4] / ncta / 1e3, (tmax - tmin) / 1e3);
   }
   if (S > 1 && !cluster_reduce) {
     const int n4b = a.H * a.W * a.ldc / 4;

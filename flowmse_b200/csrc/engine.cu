@@ -404,15 +404,9 @@ bool conv_uses_halo(const flowse_ctx* ctx, const ConvGemmArgs& a) {
          static_cast<long long>(a.B) * (a.H / 16) * (a.W / 8) * ((a.Cout + 127) / 128) >= 100;
 }
 
-int run_conv(flowse_ctx* ctx, const ConvGemmArgs& a_in, cudaStream_t s) {
+int run_conv(flowse_ctx* ctx, const ConvGemmArgs& a, cudaStream_t s) {
   std::string e;
   int rc;
-  ConvGemmArgs a = a_in;
-  const bool per_tap = ctx->conv_impl != 1 && !conv_uses_halo(ctx, a);
-  if (a.has_prep && (!per_tap || ctx->fuse_prep < 2)) {      // only the per-tap kernel can run the preparation itself
-    launch_gn_prep(a.prep, s);
-    a.has_prep = 0;
-  }
   if (ctx->conv_impl == 1) rc = launch_conv_gemm_simt(a, s, &e);
   else if (conv_uses_halo(ctx, a))
     rc = launch_conv_halo(a, ctx->conv_impl == 3 ? 3 : (ctx->conv_impl == 4 ? 2 : 1), s, &e);
@@ -513,24 +507,14 @@ struct Builder {
       pa.gamma = r.gn0_g; pa.beta = r.gn0_b;
       pa.B = B; pa.H = H; pa.W = W; pa.mode = r.down ? kPrepDown : (r.up ? kPrepUp : kPrepPlain); pa.silu = 1;
       pa.outA = fuse0 ? nullptr : scrA; pa.outX = need_x_operand ? scrX : nullptr; pa.overflow = ctx->overflow;
-      // a plain preparation in front of a per-tap conv travels with the conv (run_conv / launch_conv_gemm decide whether it
-      // becomes a phase of the conv kernel or a launch of its own)
-      if (pa.mode == kPrepPlain && !fuse0 && !conv_uses_halo(ctx, c0) && ctx->fuse_prep >= 2) {
-        c0.has_prep = 1; c0.prep = pa;
-      } else {
-        push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; }, 2);
-      }
+      push(1, [=](cudaStream_t s) { launch_gn_prep(pa, s); return 0; }, 2);
     }
     { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c0, s); }, conv_uses_halo(cx, c0) ? 7 : 3, conv_flops(c0), c0.H, c0.W, c0.ntaps * c0.Cin, c0.Cout); }
     if (!fuse1) {
       PrepArgs pb{};
       pb.src1 = h1; pb.C1 = Co; pb.src2 = nullptr; pb.C2 = 0; pb.qs1 = st1; pb.gamma = r.gn1_g; pb.beta = r.gn1_b;
       pb.B = B; pb.H = Ho; pb.W = Wo; pb.mode = kPrepPlain; pb.silu = 1; pb.outA = scrA; pb.overflow = ctx->overflow;
-      if (!conv_uses_halo(ctx, c1) && ctx->fuse_prep >= 2) {
-        c1.has_prep = 1; c1.prep = pb;
-      } else {
-        push(1, [=](cudaStream_t s) { launch_gn_prep(pb, s); return 0; }, 2);
-      }
+      push(1, [=](cudaStream_t s) { launch_gn_prep(pb, s); return 0; }, 2);
     }
     { flowse_ctx* cx = ctx; push(1, [=](cudaStream_t s) { return run_conv(cx, c1, s); }, conv_uses_halo(cx, c1) ? 7 : 3, conv_flops(c1), c1.H, c1.W, c1.ntaps * c1.Cin + c1.Cin2, c1.Cout); }
     plan->taps[mi] = out;

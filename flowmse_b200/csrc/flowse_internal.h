@@ -194,11 +194,6 @@ struct ConvGemmArgs {
   size_t splitk_scratch_elems;
   FusedOperand fA, fX;          // halo kernel: prepare the main / shortcut operand in the kernel (s1 != nullptr) instead of A / X
   unsigned long long* overflow; // optional fp16-range counter for the fused operands
-  // Per-tap kernel: the plain operand preparation that produces A (and possibly the X of a later conv) runs as a prologue
-  // phase of the conv kernel itself - the CTAs sharing an output tile prepare the tile's halo region and meet at a cluster
-  // barrier; where that is not possible launch_conv_gemm launches the standalone prep kernel first.
-  int has_prep;
-  PrepArgs prep;
 };
 constexpr size_t kSplitKScratchElems = static_cast<size_t>(148) * 128 * 128;   // enough for any one-wave split
 // returns 0 on success; fills err otherwise.

@@ -109,9 +109,7 @@ int flowse_fp16_overflow(flowse_ctx* ctx, long long* count, int reset);
  * launch of at most 148 CTAs, 4 = 2 + the halo conv launches (both measured neutral);
  * "whole_graph" 0/1 (default 1) = flowse_sample replays prior + all evaluations + updates as ONE graph from the second call
  * with a given schedule; "fuse_prep" = who prepares the conv operands (GroupNorm + SiLU + fp16 hi/lo split) of the
- * high-resolution layers: 0 a standalone pass per conv, 1 (default) the halo conv kernel itself, 2 = 1 + the plain
- * preparations of the low-resolution layers run as a prologue phase of the per-tap conv kernel (141 instead of 193 launches
- * per evaluation, bit-identical results, measured performance-neutral at B = 1 and 2 % slower at B = 4);
+ * high-resolution layers: 0 a standalone pass per conv, 1 (default) the halo conv kernel itself;
  * "spec_transform" = SpecsDataModule.transform_type used by flowse_stft_spec / flowse_spec_istft: 0 "exponent" (default),
  * 1 "log" (log(1+|X|) e^{j angle} * factor and its inverse), 2 "none" (flowmse/data_module.py:149-175);
  * "stft_window" = get_window (flowmse/data_module.py:13-19): 0 "hann" (default), 1 "sqrthann". */
