@@ -1,12 +1,12 @@
 #!/bin/bash
-# Same-box A/B: per-tap conv kernel without (pre) / with (current) the optional operand-preparation prologue phase compiled in.
+# Same-box A/B: library built with an earlier version of one source file (pre) vs the current one.
 mkdir -p gpurun_out
 run() {  # label lib batch
   FLOWSE_LIB=$PWD/flowmse_b200/$2 timeout 600 python bench.py --steps 10 --batch $3 --no-cpu-baseline --no-torch-reference --config4 0 > gpurun_out/ab9.json 2> gpurun_out/ab9.err
   python - <<PY
 import json
 d=json.load(open("gpurun_out/ab9.json"))
-print("$1 B=$3: value",round(d["value"]),"ms",round(d["ms_per_step"],3), "conv_gemm", d["roofline"]["nfe_ms_by_kernel_family"]["conv_gemm"])
+print("$1 B=$3: value",round(d["value"]),"ms",round(d["ms_per_step"],3), d["roofline"]["nfe_ms_by_kernel_family"])
 PY
 }
 for rep in 1 2 3; do
