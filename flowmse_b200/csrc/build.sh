@@ -13,5 +13,5 @@ for f in engine conv_gemm conv_halo kernels_gn kernels_pointwise sgemm stft atte
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o ../libflowse.so build/engine.o build/conv_gemm.o build/conv_halo.o build/kernels_gn.o build/kernels_pointwise.o build/sgemm.o build/stft.o build/attention.o -lcudart_static -lpthread -ldl -lrt
+$NVCC -Wno-deprecated-gpu-targets -shared -o ../libflowse.so build/engine.o build/conv_gemm.o build/conv_halo.o build/kernels_gn.o build/kernels_pointwise.o build/sgemm.o build/stft.o build/attention.o -lcudart_static -lpthread -ldl -lrt
 echo "built $(cd .. && pwd)/libflowse.so"
