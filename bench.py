@@ -387,7 +387,7 @@ def run_ours(args):
         achieved = h_fl / (h_ms * 1e-3) / 1e12
         all_conv = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
         result["roofline"] = {
-            "bound": "tensor", "kernel": "conv_halo_kernel<128,1,0> (3x3 ResBlock convolutions at 256xT, 128xT/2, 64xT/4)",
+            "bound": "tensor", "kernel": "conv_halo_kernel<128,1,0,1> (3x3 ResBlock convolutions at 256xT, 128xT/2, 64xT/4; GroupNorm + SiLU + fp16 split of the operand fused in; 4 of its 38 launches per NFE run the TMA-operand variant <128,1,0,0>)",
             "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
             "traffic": ncu_traffic.get("bytes"), "traffic_note": ncu_traffic.get("note"),
             "ncu_tensor_pipe_active_pct_of_elapsed": ncu_traffic.get("tensor_pipe_active_pct_of_elapsed"),
