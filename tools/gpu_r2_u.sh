@@ -7,7 +7,7 @@ echo "bench exit $?"
 tail -3 gpurun_out/u_bench_n$N.err
 python - <<PY
 import json
-d=json.load(open("gpurun_out/u_bench_n$N.json"))
+d=json.loads([l for l in open("gpurun_out/u_bench_n$N.json") if l.startswith("{")][-1])   # NCCL may print its version line first
 print("value",round(d["value"]),"e2e",round(d["e2e"]["value"]),"ms",round(d["ms_per_step"],3),"per-rank",d.get("per_rank_ms_per_step"))
 print("extra",d["extra"])
 PY
