@@ -10,5 +10,5 @@ for N in 1 5 25; do
   else
     timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29540 + N)) -m flowmse_b200.evaluate --folder_destination $out --synthetic_utts 824 --synthetic_weights 0 --N $N --seed 0 --max_batch_frames 4096 2>&1 | grep frames_per_s | tail -1
   fi
-  cp $out/_timing.json gpurun_out/r1b_config5_${tag}_N$N.json
+  cp $out/_timing.json gpurun_out/${PREFIX:-r1b}_config5_${tag}_N$N.json
 done
