@@ -253,6 +253,14 @@ def main(argv=None) -> Dict[str, float]:
     os.makedirs(target_dir + "files/", exist_ok=True)
     mine = sharding.lpt_assign([padded_frames(n) for n in n_samples], world)[rank]
     batches = make_batches(mine, n_samples, args.max_batch_frames)
+    # One-off start-up, kept out of the per-file timing like the reference's `model.cuda()` (evaluate.py:72-73): device
+    # context, weight upload + packing, kernel loading, STFT bases - exercised by a 1 s dummy utterance.  Reported
+    # separately (`startup_seconds`); done before the seed is set so that results for a given --seed do not depend on it.
+    t_start = time.time()
+    if dev.type == "cuda":
+        model.enhance_batch([torch.zeros(16000, device=dev) + 1e-3], N=1, odesolver=args.odesolver)
+        torch.cuda.synchronize()
+    startup = time.time() - t_start
     if args.seed is not None:
         torch.manual_seed(args.seed + rank)
 
@@ -272,7 +280,7 @@ def main(argv=None) -> Dict[str, float]:
             rows.append(dict(filename=names[i], **file_metrics(x[:m], y[:m], x_hat[:m])))
             frames_done += padded_frames(len(y))
 
-    stats = dict(rank=rank, files=len(rows), frames=frames_done, seconds=t_gpu)
+    stats = dict(rank=rank, files=len(rows), frames=frames_done, seconds=t_gpu, startup_seconds=startup)
     if world > 1:
         all_rows, all_stats = [None] * world, [None] * world
         dist.all_gather_object(all_rows, rows)
@@ -309,6 +317,7 @@ def main(argv=None) -> Dict[str, float]:
         slowest = max(s["seconds"] for s in stats_list)
         total_frames = sum(s["frames"] for s in stats_list)
         summary = dict(files=len(rows), frames=total_frames, n_gpus=world, seconds_max_rank=slowest,
+                       startup_seconds_max_rank=max(s.get("startup_seconds", 0.0) for s in stats_list),
                        frames_per_s=total_frames / slowest if slowest > 0 else float("nan"), per_rank=stats_list,
                        N=args.N, odesolver=args.odesolver)
         with open(join(target_dir, "_timing.json"), "w") as f:
