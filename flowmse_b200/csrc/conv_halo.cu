@@ -16,7 +16,8 @@
 //  * Persistent grid (one CTA per SM), static round-robin tile schedule, TMEM accumulators double-buffered
 //    (2 buffers x {main, correction} x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
 //  * Warp roles: warp 0 TMA producer (A halos + B blocks), warp 1 MMA issuer, warp 2 TMEM allocator,
-//    warps 4..11 epilogue (two per TMEM lane quadrant).
+//    warps 4..11 epilogue (two per TMEM lane quadrant; the XF variant: warps 4..7, one per quadrant, then 8 transform
+//    warps - 512 threads with 128 registers each).
 //  * PAIR variant (Cout tiles of 128): two CTAs of a cluster (one TPC) work on two M tiles with the same weights as ONE
 //    tcgen05.mma.cta_group::2 of shape 256 x 128 x 16.  Each CTA stages its own A halo and only HALF of the B block
 //    (64 of the 128 weight rows); the tensor cores read the other half from the peer's shared memory.  With the halo
