@@ -153,10 +153,12 @@ def test_conv_halo(ctx, case, impl):
     assert err < 2e-5 * max(1.0, scale), (err, scale)
 
 
-@pytest.mark.parametrize("B,H,W,mod", [(1, 16, 32, 21), (2, 16, 8, 23), (2, 4, 2, 33), (1, 4, 8, 33), (1, 16, 20, 50)])
+@pytest.mark.parametrize("B,H,W,mod", [(1, 16, 32, 21), (2, 16, 8, 23), (2, 4, 2, 33), (1, 4, 8, 33), (1, 16, 20, 50),
+                                       (4, 16, 32, 21)])
 def test_attention_block_matches_oracle(synthetic_sd, B, H, W, mod):
     """AttnBlockpp (layerspp.py:62-91) through flowse_op_attention vs the CPU oracle; token counts 512 / 128 / 8 / 32 /
-    320 exercise both SIMT GEMM tile shapes and the ragged (non multiple-of-64) paths."""
+    320 cover the ragged (non multiple-of-8) row blocks and, with the batch sizes, every rows-per-CTA variant of the two
+    kernels (core: 4 rows at B=1 x 512 tokens, 2 rows for the small blocks, 8 rows at B=4 x 512; QKV: 8 and 2 rows)."""
     from flowmse_b200.lib import Context
     c = Context(0)
     c.load_state_dict(synthetic_sd)
