@@ -110,6 +110,8 @@ int flowse_fp16_overflow(flowse_ctx* ctx, long long* count, int reset);
  * "whole_graph" 0/1 (default 1) = flowse_sample replays prior + all evaluations + updates as ONE graph from the second call
  * with a given schedule; "fuse_prep" = who prepares the conv operands (GroupNorm + SiLU + fp16 hi/lo split) of the
  * high-resolution layers: 0 a standalone pass per conv, 1 (default) the halo conv kernel itself;
+ * "fork" 0/1 (default 1) = under graph capture the pyramid heads and the input-pyramid FIR chain become parallel graph
+ * branches (nothing on the main chain needs them before the final kernel);
  * "spec_transform" = SpecsDataModule.transform_type used by flowse_stft_spec / flowse_spec_istft: 0 "exponent" (default),
  * 1 "log" (log(1+|X|) e^{j angle} * factor and its inverse), 2 "none" (flowmse/data_module.py:149-175);
  * "stft_window" = get_window (flowmse/data_module.py:13-19): 0 "hann" (default), 1 "sqrthann". */

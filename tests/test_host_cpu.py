@@ -33,6 +33,19 @@ def test_library_exports_every_declared_symbol():
     assert sorted(lib.EXPORTED_SYMBOLS) == declared
 
 
+def test_every_option_key_is_documented_in_the_header():
+    """Every key flowse_set_option accepts (engine.cu) is described in include/flowse.h."""
+    import re
+    eng = open(os.path.join(ROOT, "flowmse_b200", "csrc", "engine.cu")).read()
+    body = eng[eng.index("int flowse_set_option("):]
+    body = body[:body.index("\n}\n")]
+    keys = set(re.findall(r'k == "([a-z_0-9]+)"', body))
+    assert {"conv_impl", "fuse_prep", "graph", "pdl", "whole_graph", "fork", "stft_window", "spec_transform"} <= keys
+    hdr = open(os.path.join(ROOT, "include", "flowse.h")).read()
+    missing = [k for k in keys if f'"{k}"' not in hdr]
+    assert not missing, missing
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path must fail loudly (create returns an error, Context raises)."""
     if torch.cuda.is_available():
