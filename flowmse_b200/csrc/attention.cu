@@ -31,7 +31,15 @@ namespace {
 constexpr int kC = 256;          // channels of every attention block of the default config
 constexpr int kRMax = 8;         // most tokens (query rows) per CTA
 constexpr int kThreads = 256;
-constexpr int kStreamU = 16;     // 16-byte loads per thread and batch of the streaming loops (2 batches in flight)
+// Tunables, measured at B = 1 (same box, attention per evaluation): 16 loads per batch and >= 96 CTAs (4 rows per CTA at
+// 512 tokens) 0.200 ms; 8 loads per batch, >= 200 CTAs (2 rows per CTA, two CTAs per SM) 0.219-0.223 ms.
+#ifndef ATTN_U
+#define ATTN_U 16
+#endif
+#ifndef ATTN_MIN_CTAS
+#define ATTN_MIN_CTAS 96
+#endif
+constexpr int kStreamU = ATTN_U; // 16-byte loads per thread and batch of the streaming loops (2 batches in flight)
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -356,7 +364,7 @@ int launch_attention(const AttentionArgs& a, cudaStream_t s, std::string* err) {
   // CTAs' passes over the shared operands to spread them over the L2 slices gained 6 % of the attention time and cost
   // that property: not kept.)
   int R = kRMax;
-  while (R > 2 && static_cast<long long>((a.L + R - 1) / R) * a.B < 96) R >>= 1;
+  while (R > 2 && static_cast<long long>((a.L + R - 1) / R) * a.B < ATTN_MIN_CTAS) R >>= 1;
   const size_t smem = (static_cast<size_t>(2) * R * Lpad + static_cast<size_t>(kC) * R + static_cast<size_t>(4) * R * kC) * sizeof(float);
   if (smem > 200 * 1024) { if (err) *err = "attention: too many tokens for the shared-memory score rows"; return 1; }
   static PerDevice<bool> attr_done(false);
